@@ -1,0 +1,120 @@
+/*
+ * vsb200.h — C ABI of the B200 scan engine (libvsb200.so / vector.so).
+ *
+ * This is the drop-in boundary for sqlite-vector's brute-force scan path.  Every entry point
+ * names the reference interface it replaces (file:line relative to sqliteai/sqlite-vector 0.9.23).
+ * Plain pointers and sizes only; no C++ or torch types.  All functions return VSB_OK (0) or a
+ * negative VSB_E* code; vsb_last_error() gives the message for the calling thread.
+ *
+ * There is NO CPU fallback: without a CUDA device every scan entry point fails with VSB_ENODEV.
+ */
+#ifndef VSB200_H
+#define VSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VSB_API __attribute__((visibility("default")))
+#else
+#define VSB_API
+#endif
+
+/* element types and metrics: same numbering as the reference enums vector_type / vector_distance /
+ * vector_qtype (src/distance-cpu.h:36-58) so values can be passed through unchanged. */
+enum { VSB_F32 = 1, VSB_F16 = 2, VSB_BF16 = 3, VSB_U8 = 4, VSB_I8 = 5 };
+enum { VSB_L2 = 1, VSB_SQUARED_L2 = 2, VSB_COSINE = 3, VSB_DOT = 4, VSB_L1 = 5 };
+enum { VSB_QUANT_AUTO = 0, VSB_QUANT_U8 = 1, VSB_QUANT_S8 = 2 };
+
+enum {
+    VSB_OK = 0,
+    VSB_EINVAL = -1,  /* bad argument */
+    VSB_ENODEV = -2,  /* no CUDA device / CUDA runtime failure at start-up */
+    VSB_ENOMEM = -3,  /* host or device allocation failed */
+    VSB_ECUDA = -4,   /* a CUDA call or kernel failed */
+    VSB_ERANGE = -5   /* capacity exceeded */
+};
+
+typedef struct vsb_index vsb_index; /* one resident shard of one column on one GPU */
+
+/* A row that may enter the reference's k slots: distance (already clamped like
+ * nearly_zero_float32, src/sqlite-vector.c:994-996), its rowid and its position in scan order. */
+typedef struct vsb_candidate {
+    int64_t rowid;
+    int64_t seq;   /* global scan-order index = first_seq of the shard + local row */
+    float dist;
+    int32_t reserved;
+} vsb_candidate;
+
+/* ---- process-wide ------------------------------------------------------------------------- */
+VSB_API int vsb_device_count(void);
+VSB_API const char *vsb_last_error(void);
+/* replaces distance_backend_name (src/distance-cpu.c:20, reported by vector_backend(), :2549) */
+VSB_API const char *vsb_backend_name(void);
+
+/* ---- residency: replaces table_context.preloaded / precounter (src/sqlite-vector.c:135-136)
+ * and the staging loop of vector_quantize_preload (src/sqlite-vector.c:1338-1404) ------------- */
+/* capacity_rows is an upper bound on rows appended later; first_seq is the global scan-order index
+ * of this shard's first row (0 on a single GPU). */
+VSB_API int vsb_index_create(vsb_index **out, int device, int vtype, int dim, int64_t capacity_rows, int64_t first_seq);
+/* rows x dim elements, row-major, HOST memory; rowids NULL => rowid = first_seq + row + 1.
+ * Staged through pinned memory and copied with cudaMemcpyAsync. */
+VSB_API int vsb_index_append_dense(vsb_index *ix, const void *vectors, const int64_t *rowids, int64_t nrows);
+/* one shadow-table chunk blob: nrows x [int64 LE rowid][dim x 8-bit], the format written by
+ * vector_rebuild_quantization (src/sqlite-vector.c:1295-1311) and read back at :1382-1394.
+ * Only valid for VSB_U8 / VSB_I8 indexes. */
+VSB_API int vsb_index_append_quant_chunk(vsb_index *ix, const void *chunk, int64_t nrows);
+/* rows already in DEVICE memory of ix's GPU (dense, row pitch = dim*elem bytes); d_rowids may be NULL. */
+VSB_API int vsb_index_append_device(vsb_index *ix, const void *d_vectors, const int64_t *d_rowids, int64_t nrows);
+VSB_API int vsb_index_finalize(vsb_index *ix); /* waits for all staged copies */
+VSB_API int64_t vsb_index_rows(const vsb_index *ix);
+VSB_API int64_t vsb_index_device_bytes(const vsb_index *ix);
+VSB_API void vsb_index_free(vsb_index *ix);
+
+/* ---- the scan: replaces vFullScanRun (src/sqlite-vector.c:2071-2113) / vQuantRunMemory
+ * (:2121-2157) followed by vFullScanSortSlots (:2051-2069) ------------------------------------
+ * queries: nq x dim elements of the index's type in HOST memory (for a quantized column the caller
+ * has already quantized the query, as vQuantRun does at :2162-2177).
+ * For query b the results are out_rowids[b*k .. b*k+out_counts[b]) / out_dist[...] in the
+ * reference's output order (distance ascending, reference tie order), distances widened to
+ * double exactly like the cursor's distance[] array (:1804, :2011).
+ * max_index (in/out, may be NULL): the cursor's slot index quirk (:1808-1813 never resets it). */
+VSB_API int vsb_scan_topk(vsb_index *ix, int metric, const void *queries, int nq, int k, int64_t *out_rowids,
+                          double *out_dist, int *out_counts, int *max_index);
+
+/* every row's distance for one query, in scan order (what the *_stream modules compute one row per
+ * xNext, src/sqlite-vector.c:1901-1998).  out_dist has vsb_index_rows() floats; out_rowids may be NULL. */
+VSB_API int vsb_scan_all(vsb_index *ix, int metric, const void *query, float *out_dist, int64_t *out_rowids);
+
+/* ---- multi-GPU plumbing: each shard emits a small superset of the rows that can enter the
+ * reference's slots; the caller concatenates shards in scan order (e.g. after an NCCL all-gather)
+ * and finishes with vsb_replay_topk. -------------------------------------------------------- */
+VSB_API int vsb_scan_candidates(vsb_index *ix, int metric, const void *queries, int nq, int k, vsb_candidate *out,
+                                int cap_per_query, int *out_counts);
+/* the reference's slot algorithm over candidates in scan order: init (src/sqlite-vector.c:1808-1813),
+ * replace-the-max with first-argmax (:2022-2049, :2145-2152), exchange sort and INF trim (:2051-2069,
+ * :1816-1817).  Pure host code.  Returns the number of valid rows. */
+VSB_API int vsb_replay_topk(const vsb_candidate *cands, int n, int k, int *max_index, int64_t *out_rowids,
+                            double *out_dist);
+
+/* ---- device-resident variants used by bench.py (inputs already in HBM) --------------------- */
+/* runs the scan kernels for ONE query that is already in device memory (pitch-padded, see
+ * vsb_index_query_pitch) and leaves the candidates in the engine's output buffer; no host copies. */
+VSB_API int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k);
+/* blocks until the engine stream is idle and converts the last device-side result into top-k. */
+VSB_API int vsb_collect_last(vsb_index *ix, int k, int64_t *out_rowids, double *out_dist, int *out_count);
+VSB_API int vsb_index_query_pitch(const vsb_index *ix); /* bytes per query row on the device (multiple of 16) */
+VSB_API void *vsb_index_stream(vsb_index *ix);           /* cudaStream_t of the engine, for event timing */
+/* kernel launch counter (all kernels launched by this library since load) */
+VSB_API int64_t vsb_kernel_launches(void);
+/* tuning knobs for experiments: name in {"stage_bytes","direct","warps"}; returns previous value */
+VSB_API int vsb_set_option(const char *name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSB200_H */

@@ -1,0 +1,192 @@
+"""ctypes mirror of include/vsb200.h.  Fails loudly when the CUDA library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libvsb200.so")
+
+F32, F16, BF16, U8, I8 = 1, 2, 3, 4, 5
+L2, SQUARED_L2, COSINE, DOT, L1 = 1, 2, 3, 4, 5
+ELEM_SIZE = {F32: 4, F16: 2, BF16: 2, U8: 1, I8: 1}
+
+
+class VsbError(RuntimeError):
+    pass
+
+
+class Candidate(C.Structure):
+    _fields_ = [("rowid", C.c_int64), ("seq", C.c_int64), ("dist", C.c_float), ("reserved", C.c_int32)]
+
+
+CAND_DTYPE = np.dtype([("rowid", "<i8"), ("seq", "<i8"), ("dist", "<f4"), ("reserved", "<i4")])
+
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+
+_SIGNATURES = {
+    "vsb_device_count": (_i, []),
+    "vsb_last_error": (C.c_char_p, []),
+    "vsb_backend_name": (C.c_char_p, []),
+    "vsb_index_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i64, _i64]),
+    "vsb_index_append_dense": (_i, [_vp, _vp, _vp, _i64]),
+    "vsb_index_append_quant_chunk": (_i, [_vp, _vp, _i64]),
+    "vsb_index_append_device": (_i, [_vp, _vp, _vp, _i64]),
+    "vsb_index_finalize": (_i, [_vp]),
+    "vsb_index_rows": (_i64, [_vp]),
+    "vsb_index_device_bytes": (_i64, [_vp]),
+    "vsb_index_free": (None, [_vp]),
+    "vsb_scan_topk": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "vsb_scan_all": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "vsb_scan_candidates": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp]),
+    "vsb_replay_topk": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "vsb_scan_device_query": (_i, [_vp, _i, _vp, _i]),
+    "vsb_collect_last": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "vsb_index_query_pitch": (_i, [_vp]),
+    "vsb_index_stream": (_vp, [_vp]),
+    "vsb_kernel_launches": (_i64, []),
+    "vsb_set_option": (_i, [C.c_char_p, _i]),
+}
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, path: str = LIB_PATH):
+        if not os.path.exists(path):
+            raise VsbError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+        self.path = path
+        self.lib = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(self.lib, name)  # AttributeError => header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise VsbError(f"vsb error {rc}: {self.lib.vsb_last_error().decode()}")
+
+    def device_count(self) -> int:
+        return self.lib.vsb_device_count()
+
+    def backend_name(self) -> str:
+        return self.lib.vsb_backend_name().decode()
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.vsb_kernel_launches())
+
+    def set_option(self, name: str, value: int) -> int:
+        return self.lib.vsb_set_option(name.encode(), int(value))
+
+    def replay_topk(self, cands: np.ndarray, k: int, max_index: int = 0):
+        cands = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
+        ids = np.zeros(max(k, 1), dtype=np.int64)
+        dist = np.zeros(max(k, 1), dtype=np.float64)
+        mi = C.c_int(max_index)
+        cnt = self.lib.vsb_replay_topk(_ptr(cands), cands.shape[0], k, C.byref(mi), _ptr(ids), _ptr(dist))
+        if cnt < 0:
+            self.check(cnt)
+        return ids[:cnt].copy(), dist[:cnt].copy(), mi.value
+
+
+_ENGINE = None
+
+
+def load_engine() -> Engine:
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine()
+    return _ENGINE
+
+
+class Index:
+    """A resident shard of one column on one GPU (table_context.preloaded on the device)."""
+
+    def __init__(self, vtype: int, dim: int, capacity: int, device: int = 0, first_seq: int = 0, engine: Engine | None = None):
+        self.eng = engine or load_engine()
+        self.vtype, self.dim, self.device = vtype, dim, device
+        h = _vp()
+        self.eng.check(self.eng.lib.vsb_index_create(C.byref(h), device, vtype, dim, capacity, first_seq))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.eng.lib.vsb_index_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def rows(self) -> int:
+        return int(self.eng.lib.vsb_index_rows(self.h))
+
+    @property
+    def query_pitch(self) -> int:
+        return int(self.eng.lib.vsb_index_query_pitch(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.eng.lib.vsb_index_stream(self.h) or 0)
+
+    def append_dense(self, vectors: np.ndarray, rowids: np.ndarray | None = None):
+        assert vectors.ndim == 2 and vectors.shape[1] * vectors.itemsize == self.dim * ELEM_SIZE[self.vtype]
+        rid = None if rowids is None else np.ascontiguousarray(rowids, dtype=np.int64)
+        self.eng.check(self.eng.lib.vsb_index_append_dense(self.h, _ptr(vectors), _ptr(rid), vectors.shape[0]))
+
+    def append_quant_chunk(self, chunk: np.ndarray, nrows: int):
+        self.eng.check(self.eng.lib.vsb_index_append_quant_chunk(self.h, _ptr(chunk), nrows))
+
+    def append_device(self, d_ptr: int, nrows: int, d_rowids: int | None = None):
+        self.eng.check(self.eng.lib.vsb_index_append_device(self.h, d_ptr, d_rowids, nrows))
+
+    def finalize(self):
+        self.eng.check(self.eng.lib.vsb_index_finalize(self.h))
+
+    def scan_topk(self, metric: int, queries: np.ndarray, k: int, max_index: int | None = None):
+        q = np.ascontiguousarray(queries)
+        q2 = q.reshape(-1, q.shape[-1]) if q.ndim > 1 else q.reshape(1, -1)
+        nq = q2.shape[0]
+        ids = np.zeros((nq, max(k, 1)), dtype=np.int64)
+        dist = np.zeros((nq, max(k, 1)), dtype=np.float64)
+        counts = np.zeros(nq, dtype=np.int32)
+        mi = C.c_int(0 if max_index is None else max_index)
+        self.eng.check(self.eng.lib.vsb_scan_topk(self.h, metric, _ptr(q2), nq, k, _ptr(ids), _ptr(dist), _ptr(counts),
+                                                 C.byref(mi) if max_index is not None else None))
+        out = [(ids[b, :counts[b]].copy(), dist[b, :counts[b]].copy()) for b in range(nq)]
+        if max_index is not None:
+            return out, mi.value
+        return out
+
+    def scan_all(self, metric: int, query: np.ndarray, want_rowids: bool = False):
+        n = self.rows
+        dist = np.zeros(n, dtype=np.float32)
+        ids = np.zeros(n, dtype=np.int64) if want_rowids else None
+        self.eng.check(self.eng.lib.vsb_scan_all(self.h, metric, _ptr(np.ascontiguousarray(query)), _ptr(dist), _ptr(ids)))
+        return (dist, ids) if want_rowids else dist
+
+    def scan_candidates(self, metric: int, queries: np.ndarray, k: int, cap: int = 8192):
+        q2 = np.ascontiguousarray(queries).reshape(-1, queries.shape[-1])
+        nq = q2.shape[0]
+        out = np.zeros((nq, cap), dtype=CAND_DTYPE)
+        counts = np.zeros(nq, dtype=np.int32)
+        self.eng.check(self.eng.lib.vsb_scan_candidates(self.h, metric, _ptr(q2), nq, k, _ptr(out), cap, _ptr(counts)))
+        return [out[b, :counts[b]].copy() for b in range(nq)]
+
+    def scan_device_query(self, metric: int, d_query_ptr: int, k: int):
+        self.eng.check(self.eng.lib.vsb_scan_device_query(self.h, metric, d_query_ptr, k))
+
+    def collect_last(self, k: int):
+        ids = np.zeros(max(k, 1), dtype=np.int64)
+        dist = np.zeros(max(k, 1), dtype=np.float64)
+        cnt = C.c_int(0)
+        self.eng.check(self.eng.lib.vsb_collect_last(self.h, k, _ptr(ids), _ptr(dist), C.byref(cnt)))
+        return ids[:cnt.value].copy(), dist[:cnt.value].copy()

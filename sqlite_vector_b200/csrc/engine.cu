@@ -1,0 +1,717 @@
+// engine.cu — host side of the B200 scan engine behind include/vsb200.h.
+//
+// Owns device residency of a column shard (the GPU counterpart of table_context.preloaded,
+// /root/reference/src/sqlite-vector.c:126-137, filled by vector_quantize_preload :1338-1404),
+// launches the sm_100a kernels in scan_kernels.cuh and finishes each query with the reference's
+// k-slot algorithm (:1808-1817, :2022-2069, :2145-2152) over the few hundred surviving candidates.
+// No CPU fallback: if CUDA is unavailable every entry point returns VSB_ENODEV.
+#include "../../include/vsb200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "scan_kernels.cuh"
+
+using namespace vsb;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+int g_opt_stage_bytes = 8192;  // target bytes of one warp tile (ring stage)
+int g_opt_direct = 0;          // 1: force the no-staging kernel
+int g_opt_ring_bytes = 0;      // 0: use all shared memory left
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(e_ == cudaErrorMemoryAllocation ? VSB_ENOMEM : VSB_ECUDA, "%s failed: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                                \
+    } while (0)
+
+int elem_size(int vtype) {
+    switch (vtype) {
+    case VSB_F32: return 4;
+    case VSB_F16: case VSB_BF16: return 2;
+    case VSB_U8: case VSB_I8: return 1;
+    }
+    return 0;
+}
+
+constexpr size_t kStageBuf = 32u << 20;  // pinned staging buffers for preload (two of them)
+constexpr int kOutCap = 1 << 16;         // survivor capacity per query (mapped pinned)
+constexpr int kMaxK = 256;               // candidate path; larger k uses the all-distances path
+constexpr int kSlots = 2;                // result slots (pipelining of batches)
+
+struct Slot {
+    uint2 *h_out = nullptr, *d_out = nullptr;  // mapped pinned survivors
+    int2 *h_table = nullptr, *d_table = nullptr;
+    int *h_hdr = nullptr, *d_hdr = nullptr;
+    uint8_t *h_query = nullptr, *d_query = nullptr;  // pinned staging + device copy of the query
+    int *d_ctrl = nullptr;
+    int seq = 0;
+    int nblocks = 0;
+};
+
+}  // namespace
+
+struct vsb_index {
+    int device = 0, vtype = 0, dim = 0, esize = 0, pitch = 0;
+    long long cap = 0, n = 0, first_seq = 0;
+    uint8_t *d_vec = nullptr;
+    bool implicit_ids = true;
+    std::vector<int64_t> h_rowids;
+    cudaStream_t stream = nullptr;
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    int stage_next = 0;
+    int num_sms = 0, max_smem = 0;
+    // scan workspace
+    int ws_kcap = 0, ws_logcap = 0, ws_streams = 0;
+    float *d_lists = nullptr;
+    uint2 *d_logs = nullptr;
+    int *d_counts = nullptr;
+    Slot slot[kSlots];
+    bool slots_ready = false;
+    float *d_dist_all = nullptr;
+    int last_slot = -1, last_metric = 0;
+    size_t dev_bytes = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------ kernel dispatch
+using ScanFn = void (*)(const ScanParams);
+template <int VT, int MC, bool D>
+ScanFn fn_of() { return scan_kernel<VT, MC, D>; }
+
+ScanFn pick_kernel(int vtype, int mc, bool direct) {
+#define ROW(VT)                                                                                                   \
+    case VT:                                                                                                      \
+        switch (mc) {                                                                                             \
+        case MC_L2: return direct ? fn_of<VT, MC_L2, true>() : fn_of<VT, MC_L2, false>();                         \
+        case MC_COS: return direct ? fn_of<VT, MC_COS, true>() : fn_of<VT, MC_COS, false>();                      \
+        case MC_DOT: return direct ? fn_of<VT, MC_DOT, true>() : fn_of<VT, MC_DOT, false>();                      \
+        case MC_L1: return direct ? fn_of<VT, MC_L1, true>() : fn_of<VT, MC_L1, false>();                         \
+        }                                                                                                         \
+        break;
+    switch (vtype) {
+        ROW(T_F32) ROW(T_F16) ROW(T_BF16) ROW(T_U8) ROW(T_I8)
+    }
+#undef ROW
+    return nullptr;
+}
+
+int metric_class(int metric, int *root) {
+    *root = 0;
+    switch (metric) {
+    case VSB_L2: *root = 1; return MC_L2;
+    case VSB_SQUARED_L2: return MC_L2;
+    case VSB_COSINE: return MC_COS;
+    case VSB_DOT: return MC_DOT;
+    case VSB_L1: return MC_L1;
+    }
+    return -1;
+}
+
+struct Plan {
+    bool direct;
+    int log2P, wtile_bytes, nsw;
+    size_t smem;
+};
+
+// choose lanes-per-row, ring depth and shared-memory size for (pitch, kcap)
+Plan make_plan(const vsb_index *ix, int kcap) {
+    Plan pl{};
+    const int pitch = ix->pitch;
+    int log2P = 0;
+    while (log2P < 5 && (32 >> log2P) * (long long)pitch > g_opt_stage_bytes) ++log2P;
+    const size_t fixed = kBarrierBytes + (((size_t)pitch + (size_t)kWarps * kcap * 4 + 127) & ~(size_t)127);
+    size_t avail = (size_t)ix->max_smem > fixed ? (size_t)ix->max_smem - fixed : 0;
+    if (g_opt_ring_bytes > 0 && (size_t)g_opt_ring_bytes < avail) avail = (size_t)g_opt_ring_bytes;
+    const size_t wtile = (size_t)(32 >> log2P) * pitch;
+    int nsw = (int)(avail / kWarps / (wtile ? wtile : 1));
+    if (nsw > kMaxStages) nsw = kMaxStages;
+    pl.direct = g_opt_direct || nsw < 2;
+    if (pl.direct) {
+        pl.log2P = 5;  // a whole warp per row, coalesced 16-byte loads straight from HBM
+        pl.wtile_bytes = pitch;
+        pl.nsw = 1;
+        pl.smem = fixed;
+    } else {
+        pl.log2P = log2P;
+        pl.wtile_bytes = (int)wtile;
+        pl.nsw = nsw;
+        pl.smem = fixed + (size_t)kWarps * nsw * wtile;
+    }
+    return pl;
+}
+
+int ensure_slots(vsb_index *ix) {
+    if (ix->slots_ready) return VSB_OK;
+    for (int i = 0; i < kSlots; ++i) {
+        Slot &s = ix->slot[i];
+        CU(cudaHostAlloc((void **)&s.h_out, sizeof(uint2) * kOutCap, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void **)&s.d_out, s.h_out, 0));
+        CU(cudaHostAlloc((void **)&s.h_table, sizeof(int2) * 4096, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void **)&s.d_table, s.h_table, 0));
+        CU(cudaHostAlloc((void **)&s.h_hdr, sizeof(int) * 16, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void **)&s.d_hdr, s.h_hdr, 0));
+        memset(s.h_hdr, 0, sizeof(int) * 16);
+        CU(cudaHostAlloc((void **)&s.h_query, (size_t)ix->pitch, cudaHostAllocDefault));
+        CU(cudaMalloc((void **)&s.d_query, (size_t)ix->pitch));
+        CU(cudaMalloc((void **)&s.d_ctrl, sizeof(int) * 4));
+        CU(cudaMemset(s.d_ctrl, 0, sizeof(int) * 4));
+    }
+    ix->slots_ready = true;
+    return VSB_OK;
+}
+
+int ensure_workspace(vsb_index *ix, int k) {
+    const int kcap = (k + 31) & ~31;
+    const int logcap = std::max(256, 12 * k);
+    const int streams = ix->num_sms * kWarps;
+    if (ix->ws_kcap >= kcap && ix->ws_logcap >= logcap && ix->ws_streams == streams) return VSB_OK;
+    if (ix->d_lists) cudaFree(ix->d_lists);
+    if (ix->d_logs) cudaFree(ix->d_logs);
+    if (ix->d_counts) cudaFree(ix->d_counts);
+    ix->d_lists = nullptr; ix->d_logs = nullptr; ix->d_counts = nullptr;
+    ix->ws_kcap = 0;
+    CU(cudaMalloc((void **)&ix->d_lists, sizeof(float) * (size_t)streams * kcap));
+    CU(cudaMalloc((void **)&ix->d_logs, sizeof(uint2) * (size_t)streams * logcap));
+    CU(cudaMalloc((void **)&ix->d_counts, sizeof(int) * (size_t)streams));
+    ix->ws_kcap = kcap; ix->ws_logcap = logcap; ix->ws_streams = streams;
+    return VSB_OK;
+}
+
+// launches scan (+ filter when k > 0) for the query in `d_query` (pitch bytes) on ix->stream
+int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *slot, float *d_dist_all) {
+    int root = 0;
+    const int mc = metric_class(metric, &root);
+    if (mc < 0) return fail(VSB_EINVAL, "unknown distance metric %d", metric);
+    const int kcap = k > 0 ? ix->ws_kcap : 0;
+    const Plan pl = make_plan(ix, kcap);
+    ScanFn fn = pick_kernel(ix->vtype, mc, pl.direct);
+    if (!fn) return fail(VSB_EINVAL, "unsupported vector type %d", ix->vtype);
+    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+
+    ScanParams p{};
+    p.vec = ix->d_vec;
+    p.n = ix->n;
+    p.pitch = ix->pitch;
+    p.nc = ix->pitch / 16;
+    p.log2P = pl.log2P;
+    p.wtile_bytes = pl.wtile_bytes;
+    p.nsw = pl.nsw;
+    p.query = d_query;
+    p.root = root;
+    p.k = k;
+    p.kcap = kcap;
+    p.lists = ix->d_lists;
+    p.logs = ix->d_logs;
+    p.counts = ix->d_counts;
+    p.logcap = ix->ws_logcap;
+    p.ctrl = slot ? slot->d_ctrl : nullptr;
+    p.dist_all = d_dist_all;
+    fn<<<ix->num_sms, kThreads, pl.smem, ix->stream>>>(p);
+    CU(cudaGetLastError());
+    ++g_launches;
+    if (k > 0) {
+        FilterParams f{};
+        f.S = ix->ws_streams;
+        f.k = k;
+        f.kcap = kcap;
+        f.lists = ix->d_lists;
+        f.logs = ix->d_logs;
+        f.counts = ix->d_counts;
+        f.logcap = ix->ws_logcap;
+        f.out = slot->d_out;
+        f.outcap = kOutCap;
+        f.table = slot->d_table;
+        f.hdr = slot->d_hdr;
+        f.ctrl = slot->d_ctrl;
+        f.seqno = ++slot->seq;
+        const int nblocks = (f.S + kFilterWarps - 1) / kFilterWarps;
+        slot->nblocks = nblocks;
+        const size_t fsm = sizeof(float) * ((size_t)2 * kFilterWarps * kcap + (size_t)f.S + 32);
+        CU(cudaFuncSetAttribute((const void *)filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+        filter_kernel<<<nblocks, kFilterWarps * 32, fsm, ix->stream>>>(f);
+        CU(cudaGetLastError());
+        ++g_launches;
+    }
+    return VSB_OK;
+}
+
+inline int64_t rowid_of(const vsb_index *ix, uint32_t local) {
+    return ix->implicit_ids ? (int64_t)(ix->first_seq + (long long)local + 1) : ix->h_rowids[local];
+}
+
+// ------------------------------------------------------------------ the reference's k-slot algorithm
+struct SlotState {
+    int k, mi;
+    double *dist;
+    int64_t *ids;
+};
+inline int first_max(const double *v, int n) {  // first index of the maximum, strict '>' (:2022-2049)
+    int b = 0;
+    for (int i = 1; i < n; ++i)
+        if (v[i] > v[b]) b = i;
+    return b;
+}
+inline void slots_begin(SlotState &s) {  // :1808-1813 (max_index is carried over, not reset)
+    for (int i = 0; i < s.k; ++i) { s.dist[i] = std::numeric_limits<double>::infinity(); s.ids[i] = 0; }
+    if (s.mi < 0 || s.mi >= s.k) s.mi = 0;
+}
+inline void slots_offer(SlotState &s, float d, int64_t id) {  // :2102-2106 / :2145-2152
+    if ((double)d < s.dist[s.mi]) {
+        s.dist[s.mi] = (double)d;
+        s.ids[s.mi] = id;
+        s.mi = first_max(s.dist, s.k);
+    }
+}
+inline int slots_finish(SlotState &s) {  // exchange sort + INF trim (:2051-2069, :1816-1817)
+    const double inf = std::numeric_limits<double>::infinity();
+    int unused = 0;
+    for (int i = 0; i + 1 < s.k; ++i) {
+        if (s.dist[i] == inf) ++unused;
+        for (int j = i + 1; j < s.k; ++j)
+            if (s.dist[j] < s.dist[i]) { std::swap(s.dist[i], s.dist[j]); std::swap(s.ids[i], s.ids[j]); }
+    }
+    if (s.dist[s.k - 1] == inf) ++unused;
+    return s.k - unused;
+}
+
+// gather the survivors of a finished slot in scan order; returns count or <0
+int gather_survivors(vsb_index *ix, Slot *slot, std::vector<uint2> &out, bool *overflow) {
+    *overflow = false;
+    if (slot->h_hdr[2] != slot->seq) return fail(VSB_ECUDA, "scan result header not published (seq %d != %d)", slot->h_hdr[2], slot->seq);
+    if (slot->h_hdr[1]) { *overflow = true; return 0; }
+    const int total = slot->h_hdr[0];
+    out.clear();
+    out.reserve((size_t)total);
+    for (int b = 0; b < slot->nblocks; ++b) {
+        const int2 t = slot->h_table[b];
+        for (int i = 0; i < t.y; ++i) out.push_back(slot->h_out[t.x + i]);
+    }
+    (void)ix;
+    return (int)out.size();
+}
+
+int scan_all_into(vsb_index *ix, int metric, const uint8_t *d_query, std::vector<float> &dist) {
+    if (!ix->d_dist_all) {
+        CU(cudaMalloc((void **)&ix->d_dist_all, sizeof(float) * (size_t)std::max<long long>(ix->cap, 1)));
+        ix->dev_bytes += sizeof(float) * (size_t)ix->cap;
+    }
+    int rc = launch_scan(ix, metric, d_query, 0, nullptr, ix->d_dist_all);
+    if (rc) return rc;
+    dist.resize((size_t)ix->n);
+    CU(cudaMemcpyAsync(dist.data(), ix->d_dist_all, sizeof(float) * (size_t)ix->n, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+    return VSB_OK;
+}
+
+int stage_query(vsb_index *ix, Slot *slot, const void *query) {
+    const int qbytes = ix->dim * ix->esize;
+    memcpy(slot->h_query, query, (size_t)qbytes);
+    if (ix->pitch > qbytes) memset(slot->h_query + qbytes, 0, (size_t)(ix->pitch - qbytes));
+    CU(cudaMemcpyAsync(slot->d_query, slot->h_query, (size_t)ix->pitch, cudaMemcpyHostToDevice, ix->stream));
+    return VSB_OK;
+}
+
+// one query, host in / candidates out (sorted by scan order).  Falls back to the all-distances kernel when the
+// candidate log overflowed or k is larger than the candidate path supports (still GPU-computed distances).
+int query_candidates(vsb_index *ix, int metric, const void *query, int k, std::vector<uint2> &cands) {
+    CU(cudaSetDevice(ix->device));
+    int rc = ensure_slots(ix);
+    if (rc) return rc;
+    Slot *slot = &ix->slot[0];
+    rc = stage_query(ix, slot, query);
+    if (rc) return rc;
+    bool overflow = (k > kMaxK);
+    if (!overflow) {
+        rc = ensure_workspace(ix, k);
+        if (rc) return rc;
+        rc = launch_scan(ix, metric, slot->d_query, k, slot, nullptr);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ix->stream));
+        int n = gather_survivors(ix, slot, cands, &overflow);
+        if (n < 0) return n;
+    }
+    if (overflow) {
+        std::vector<float> dist;
+        rc = scan_all_into(ix, metric, slot->d_query, dist);
+        if (rc) return rc;
+        cands.resize((size_t)ix->n);
+        for (long long i = 0; i < ix->n; ++i) {
+            uint32_t bits;
+            memcpy(&bits, &dist[(size_t)i], 4);
+            cands[(size_t)i] = make_uint2(bits, (uint32_t)i);
+        }
+    }
+    return VSB_OK;
+}
+
+int check_index(const vsb_index *ix) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    return VSB_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int vsb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *vsb_last_error(void) { return g_err.c_str(); }
+
+const char *vsb_backend_name(void) {
+    static std::once_flag once;
+    static char name[160];
+    std::call_once(once, [] {
+        int n = vsb_device_count();
+        if (n <= 0) { snprintf(name, sizeof name, "CUDA sm_100a (no device)"); return; }
+        cudaDeviceProp pr{};
+        cudaGetDeviceProperties(&pr, 0);
+        snprintf(name, sizeof name, "CUDA sm_100a (%s x%d, cc %d.%d)", pr.name, n, pr.major, pr.minor);
+    });
+    return name;
+}
+
+int64_t vsb_kernel_launches(void) { return g_launches.load(); }
+
+int vsb_set_option(const char *name, int value) {
+    int *p = nullptr;
+    if (!strcmp(name, "stage_bytes")) p = &g_opt_stage_bytes;
+    else if (!strcmp(name, "direct")) p = &g_opt_direct;
+    else if (!strcmp(name, "ring_bytes")) p = &g_opt_ring_bytes;
+    if (!p) return fail(VSB_EINVAL, "unknown option %s", name);
+    int old = *p;
+    *p = value;
+    return old;
+}
+
+int vsb_index_create(vsb_index **out, int device, int vtype, int dim, int64_t capacity_rows, int64_t first_seq) {
+    if (!out) return fail(VSB_EINVAL, "out is null");
+    *out = nullptr;
+    const int es = elem_size(vtype);
+    if (!es) return fail(VSB_EINVAL, "unknown vector type %d", vtype);
+    if (dim <= 0) return fail(VSB_EINVAL, "dimension must be positive");
+    if (capacity_rows < 0 || capacity_rows > 0xFFFFFFF0ll) return fail(VSB_EINVAL, "capacity_rows out of range");
+    int ndev = vsb_device_count();
+    if (ndev <= 0) return fail(VSB_ENODEV, "no CUDA device available (this build has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(VSB_EINVAL, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp pr{};
+    CU(cudaGetDeviceProperties(&pr, device));
+    if (pr.major < 9) return fail(VSB_ENODEV, "device %s (cc %d.%d) lacks TMA bulk copies; sm_100a required", pr.name, pr.major, pr.minor);
+    vsb_index *ix = new (std::nothrow) vsb_index();
+    if (!ix) return fail(VSB_ENOMEM, "out of host memory");
+    ix->device = device; ix->vtype = vtype; ix->dim = dim; ix->esize = es;
+    ix->pitch = (dim * es + 15) & ~15;
+    ix->cap = capacity_rows; ix->first_seq = first_seq;
+    ix->num_sms = pr.multiProcessorCount;
+    ix->max_smem = (int)pr.sharedMemPerBlockOptin;
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ix; return fail(VSB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    const size_t bytes = (size_t)std::max<long long>(capacity_rows, 1) * ix->pitch + 1024;
+    e = cudaMalloc((void **)&ix->d_vec, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamDestroy(ix->stream);
+        delete ix;
+        return fail(VSB_ENOMEM, "cudaMalloc(%zu bytes) for the resident column failed: %s", bytes, cudaGetErrorString(e));
+    }
+    ix->dev_bytes = bytes;
+    *out = ix;
+    return VSB_OK;
+}
+
+static int stage_acquire(vsb_index *ix, int *which) {
+    const int b = ix->stage_next;
+    if (!ix->stage[b]) {
+        CU(cudaHostAlloc((void **)&ix->stage[b], kStageBuf, cudaHostAllocDefault));
+        CU(cudaEventCreateWithFlags(&ix->stage_ev[b], cudaEventDisableTiming));
+    } else {
+        CU(cudaEventSynchronize(ix->stage_ev[b]));  // previous copy out of this buffer finished
+    }
+    ix->stage_next ^= 1;
+    *which = b;
+    return VSB_OK;
+}
+
+// src_stride: bytes between rows in host memory; src_off: offset of the vector inside a row
+static int append_rows(vsb_index *ix, const uint8_t *src, size_t src_stride, size_t src_off, const int64_t *rowids,
+                       bool ids_inline, int64_t nrows) {
+    if (nrows < 0) return fail(VSB_EINVAL, "negative row count");
+    if (ix->n + nrows > ix->cap) return fail(VSB_ERANGE, "index capacity exceeded (%lld + %lld > %lld)", ix->n, (long long)nrows, ix->cap);
+    CU(cudaSetDevice(ix->device));
+    const size_t rowbytes = (size_t)ix->dim * ix->esize;
+    const size_t pitch = (size_t)ix->pitch;
+    const bool have_ids = ids_inline || rowids != nullptr;
+    if (have_ids && ix->implicit_ids) {
+        // materialise the implicit ids of rows appended so far
+        ix->h_rowids.resize((size_t)ix->n);
+        for (long long i = 0; i < ix->n; ++i) ix->h_rowids[(size_t)i] = ix->first_seq + i + 1;
+        ix->implicit_ids = false;
+    }
+    const int64_t per_buf = (int64_t)(kStageBuf / pitch);
+    int64_t done = 0;
+    while (done < nrows) {
+        const int64_t m = std::min<int64_t>(per_buf, nrows - done);
+        int b;
+        int rc = stage_acquire(ix, &b);
+        if (rc) return rc;
+        uint8_t *dst = ix->stage[b];
+        for (int64_t r = 0; r < m; ++r) {
+            const uint8_t *row = src + (size_t)(done + r) * src_stride;
+            memcpy(dst + (size_t)r * pitch, row + src_off, rowbytes);
+            if (pitch > rowbytes) memset(dst + (size_t)r * pitch + rowbytes, 0, pitch - rowbytes);
+            if (ids_inline) {
+                uint64_t v = 0;  // little-endian int64 rowid in front of the vector (INT64_FROM_INT8PTR, :86-94)
+                for (int i = 7; i >= 0; --i) v = (v << 8) | row[i];
+                ix->h_rowids.push_back((int64_t)v);
+            }
+        }
+        CU(cudaMemcpyAsync(ix->d_vec + (size_t)(ix->n + done) * pitch, dst, (size_t)m * pitch, cudaMemcpyHostToDevice, ix->stream));
+        CU(cudaEventRecord(ix->stage_ev[b], ix->stream));
+        done += m;
+    }
+    if (!ids_inline) {
+        if (rowids) ix->h_rowids.insert(ix->h_rowids.end(), rowids, rowids + nrows);
+        else if (!ix->implicit_ids)
+            for (int64_t r = 0; r < nrows; ++r) ix->h_rowids.push_back(ix->first_seq + ix->n + r + 1);
+    }
+    ix->n += nrows;
+    return VSB_OK;
+}
+
+int vsb_index_append_dense(vsb_index *ix, const void *vectors, const int64_t *rowids, int64_t nrows) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (!vectors && nrows > 0) return fail(VSB_EINVAL, "vectors is null");
+    return append_rows(ix, (const uint8_t *)vectors, (size_t)ix->dim * ix->esize, 0, rowids, false, nrows);
+}
+
+int vsb_index_append_quant_chunk(vsb_index *ix, const void *chunk, int64_t nrows) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (ix->esize != 1) return fail(VSB_EINVAL, "quantized chunks need a UINT8/INT8 index");
+    if (!chunk && nrows > 0) return fail(VSB_EINVAL, "chunk is null");
+    return append_rows(ix, (const uint8_t *)chunk, (size_t)ix->dim + 8, 8, nullptr, true, nrows);
+}
+
+int vsb_index_append_device(vsb_index *ix, const void *d_vectors, const int64_t *d_rowids, int64_t nrows) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (nrows < 0 || ix->n + nrows > ix->cap) return fail(VSB_ERANGE, "index capacity exceeded");
+    CU(cudaSetDevice(ix->device));
+    const size_t rowbytes = (size_t)ix->dim * ix->esize;
+    if ((size_t)ix->pitch != rowbytes)
+        CU(cudaMemsetAsync(ix->d_vec + (size_t)ix->n * ix->pitch, 0, (size_t)nrows * ix->pitch, ix->stream));
+    CU(cudaMemcpy2DAsync(ix->d_vec + (size_t)ix->n * ix->pitch, (size_t)ix->pitch, d_vectors, rowbytes, rowbytes, (size_t)nrows,
+                         cudaMemcpyDeviceToDevice, ix->stream));
+    if (d_rowids) {
+        if (ix->implicit_ids) {
+            ix->h_rowids.resize((size_t)ix->n);
+            for (long long i = 0; i < ix->n; ++i) ix->h_rowids[(size_t)i] = ix->first_seq + i + 1;
+            ix->implicit_ids = false;
+        }
+        ix->h_rowids.resize((size_t)(ix->n + nrows));
+        CU(cudaMemcpyAsync(ix->h_rowids.data() + ix->n, d_rowids, sizeof(int64_t) * (size_t)nrows, cudaMemcpyDeviceToHost, ix->stream));
+    } else if (!ix->implicit_ids) {
+        for (int64_t r = 0; r < nrows; ++r) ix->h_rowids.push_back(ix->first_seq + ix->n + r + 1);
+    }
+    CU(cudaStreamSynchronize(ix->stream));
+    ix->n += nrows;
+    return VSB_OK;
+}
+
+int vsb_index_finalize(vsb_index *ix) {
+    if (check_index(ix)) return VSB_EINVAL;
+    CU(cudaSetDevice(ix->device));
+    CU(cudaStreamSynchronize(ix->stream));
+    for (int b = 0; b < 2; ++b) {  // the staging buffers are only needed while loading
+        if (ix->stage[b]) { cudaFreeHost(ix->stage[b]); ix->stage[b] = nullptr; }
+        if (ix->stage_ev[b]) { cudaEventDestroy(ix->stage_ev[b]); ix->stage_ev[b] = nullptr; }
+    }
+    return VSB_OK;
+}
+
+int64_t vsb_index_rows(const vsb_index *ix) { return ix ? ix->n : 0; }
+int64_t vsb_index_device_bytes(const vsb_index *ix) { return ix ? (int64_t)ix->dev_bytes : 0; }
+int vsb_index_query_pitch(const vsb_index *ix) { return ix ? ix->pitch : 0; }
+void *vsb_index_stream(vsb_index *ix) { return ix ? (void *)ix->stream : nullptr; }
+
+void vsb_index_free(vsb_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    for (int b = 0; b < 2; ++b) {
+        if (ix->stage[b]) cudaFreeHost(ix->stage[b]);
+        if (ix->stage_ev[b]) cudaEventDestroy(ix->stage_ev[b]);
+    }
+    for (int i = 0; i < kSlots; ++i) {
+        Slot &s = ix->slot[i];
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.h_table) cudaFreeHost(s.h_table);
+        if (s.h_hdr) cudaFreeHost(s.h_hdr);
+        if (s.h_query) cudaFreeHost(s.h_query);
+        if (s.d_query) cudaFree(s.d_query);
+        if (s.d_ctrl) cudaFree(s.d_ctrl);
+    }
+    if (ix->d_lists) cudaFree(ix->d_lists);
+    if (ix->d_logs) cudaFree(ix->d_logs);
+    if (ix->d_counts) cudaFree(ix->d_counts);
+    if (ix->d_dist_all) cudaFree(ix->d_dist_all);
+    if (ix->d_vec) cudaFree(ix->d_vec);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+int vsb_scan_topk(vsb_index *ix, int metric, const void *queries, int nq, int k, int64_t *out_rowids, double *out_dist,
+                  int *out_counts, int *max_index) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (!queries || nq < 0 || k < 0) return fail(VSB_EINVAL, "bad scan arguments");
+    if (k == 0) {  // k == 0 yields an empty result (src/sqlite-vector.c:1795-1796)
+        for (int b = 0; b < nq; ++b) if (out_counts) out_counts[b] = 0;
+        return VSB_OK;
+    }
+    if (!out_rowids || !out_dist) return fail(VSB_EINVAL, "output buffers are null");
+    const size_t qbytes = (size_t)ix->dim * ix->esize;
+    std::vector<uint2> cands;
+    int mi = max_index ? *max_index : 0;
+    for (int b = 0; b < nq; ++b) {
+        int rc = query_candidates(ix, metric, (const uint8_t *)queries + (size_t)b * qbytes, k, cands);
+        if (rc) return rc;
+        SlotState s{k, mi, out_dist + (size_t)b * k, out_rowids + (size_t)b * k};
+        slots_begin(s);
+        for (const uint2 &c : cands) {
+            float d;
+            memcpy(&d, &c.x, 4);
+            slots_offer(s, d, rowid_of(ix, c.y));
+        }
+        mi = s.mi;
+        const int cnt = slots_finish(s);
+        if (out_counts) out_counts[b] = cnt;
+    }
+    if (max_index) *max_index = mi;
+    return VSB_OK;
+}
+
+int vsb_scan_all(vsb_index *ix, int metric, const void *query, float *out_dist, int64_t *out_rowids) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (!query || !out_dist) return fail(VSB_EINVAL, "bad scan arguments");
+    CU(cudaSetDevice(ix->device));
+    int rc = ensure_slots(ix);
+    if (rc) return rc;
+    rc = stage_query(ix, &ix->slot[0], query);
+    if (rc) return rc;
+    std::vector<float> dist;
+    rc = scan_all_into(ix, metric, ix->slot[0].d_query, dist);
+    if (rc) return rc;
+    memcpy(out_dist, dist.data(), sizeof(float) * (size_t)ix->n);
+    if (out_rowids)
+        for (long long i = 0; i < ix->n; ++i) out_rowids[i] = rowid_of(ix, (uint32_t)i);
+    return VSB_OK;
+}
+
+int vsb_scan_candidates(vsb_index *ix, int metric, const void *queries, int nq, int k, vsb_candidate *out, int cap_per_query,
+                        int *out_counts) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (!queries || !out || !out_counts || nq < 0 || k <= 0 || cap_per_query <= 0) return fail(VSB_EINVAL, "bad scan arguments");
+    const size_t qbytes = (size_t)ix->dim * ix->esize;
+    std::vector<uint2> cands;
+    for (int b = 0; b < nq; ++b) {
+        int rc = query_candidates(ix, metric, (const uint8_t *)queries + (size_t)b * qbytes, k, cands);
+        if (rc) return rc;
+        if ((int)cands.size() > cap_per_query) {
+            // too many to ship: reduce on this shard first (the shard-local replay keeps exactly the rows
+            // that survive locally; a superset of what can survive globally is NOT guaranteed by truncation,
+            // so instead we report the condition)
+            return fail(VSB_ERANGE, "query %d produced %zu candidates (> cap %d)", b, cands.size(), cap_per_query);
+        }
+        vsb_candidate *o = out + (size_t)b * cap_per_query;
+        for (size_t i = 0; i < cands.size(); ++i) {
+            memcpy(&o[i].dist, &cands[i].x, 4);
+            o[i].rowid = rowid_of(ix, cands[i].y);
+            o[i].seq = ix->first_seq + (long long)cands[i].y;
+            o[i].reserved = 0;
+        }
+        out_counts[b] = (int)cands.size();
+    }
+    return VSB_OK;
+}
+
+int vsb_replay_topk(const vsb_candidate *cands, int n, int k, int *max_index, int64_t *out_rowids, double *out_dist) {
+    if (k <= 0) return 0;
+    if ((!cands && n > 0) || !out_rowids || !out_dist) return fail(VSB_EINVAL, "bad replay arguments");
+    SlotState s{k, max_index ? *max_index : 0, out_dist, out_rowids};
+    slots_begin(s);
+    for (int i = 0; i < n; ++i) slots_offer(s, cands[i].dist, cands[i].rowid);
+    if (max_index) *max_index = s.mi;
+    return slots_finish(s);
+}
+
+int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (!d_query || k <= 0 || k > kMaxK) return fail(VSB_EINVAL, "bad device scan arguments (k must be 1..%d)", kMaxK);
+    CU(cudaSetDevice(ix->device));
+    int rc = ensure_slots(ix);
+    if (rc) return rc;
+    rc = ensure_workspace(ix, k);
+    if (rc) return rc;
+    const int si = (ix->last_slot + 1) % kSlots;
+    rc = launch_scan(ix, metric, (const uint8_t *)d_query, k, &ix->slot[si], nullptr);
+    if (rc) return rc;
+    ix->last_slot = si;
+    ix->last_metric = metric;
+    return VSB_OK;
+}
+
+int vsb_collect_last(vsb_index *ix, int k, int64_t *out_rowids, double *out_dist, int *out_count) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (ix->last_slot < 0) return fail(VSB_EINVAL, "no device scan was launched");
+    CU(cudaSetDevice(ix->device));
+    CU(cudaStreamSynchronize(ix->stream));
+    std::vector<uint2> cands;
+    bool overflow = false;
+    int n = gather_survivors(ix, &ix->slot[ix->last_slot], cands, &overflow);
+    if (n < 0) return n;
+    if (overflow) return fail(VSB_ERANGE, "candidate log overflowed; use vsb_scan_topk (host query) for this input");
+    SlotState s{k, 0, out_dist, out_rowids};
+    slots_begin(s);
+    for (const uint2 &c : cands) {
+        float d;
+        memcpy(&d, &c.x, 4);
+        slots_offer(s, d, rowid_of(ix, c.y));
+    }
+    const int cnt = slots_finish(s);
+    if (out_count) *out_count = cnt;
+    return VSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,574 @@
+// scan_kernels.cuh — sm_100a kernels of the single-query (HBM-bound) distance scan.
+//
+// Replaces, for a whole resident shard at once, the per-row loop of the reference:
+//   fn = dispatch_distance_table[metric][type]; d = fn(q,row,dim); clamp; slot update
+//   (/root/reference/src/sqlite-vector.c:2089-2107 and :2138-2153, kernels in src/distance-cpu.c:39-693).
+//
+// Design:
+//   * corpus rows are dense in HBM ([n][pitch], pitch = dim*elt rounded up to 16 B, zero padded);
+//   * every WARP owns a contiguous range of rows ("stream") and pulls it through its own ring of
+//     shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) that it issues
+//     itself — no block-level barrier anywhere in the steady state;
+//   * P = 1..32 lanes cooperate on a row; 16-byte LDS with a per-row rotation keeps the shared-memory
+//     reads conflict-free; integer types use dp4a / vabsdiff4 (exact int32), fp types FFMA;
+//   * top-k: each warp keeps the k smallest distances of its own stream in shared memory and logs every
+//     row that beats the running k-th value (strict <).  That log is a superset of the rows that can
+//     ever enter the reference's k slots; filter_kernel tightens it with prefix thresholds and the
+//     host replays the reference's slot algorithm over the few hundred survivors, which reproduces
+//     the reference's history-dependent tie handling exactly.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+namespace vsb {
+
+constexpr int kWarps = 8;             // consumer warps per CTA (each one is a stream)
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxStages = 8;         // ring stages per warp
+constexpr int kBarrierBytes = 1024;   // reserved at the start of dynamic smem for mbarriers + scalars
+
+enum { T_F32 = 1, T_F16 = 2, T_BF16 = 3, T_U8 = 4, T_I8 = 5 };
+enum { MC_L2 = 0, MC_COS = 1, MC_DOT = 2, MC_L1 = 3 };  // L2 and SQUARED_L2 share a kernel (root flag)
+
+struct ScanParams {
+    const uint8_t *vec;   // [n][pitch]
+    long long n;
+    int pitch;            // bytes per row (multiple of 16)
+    int nc;               // 16-byte chunks per row
+    int log2P;            // lanes per row = 1 << log2P
+    int wtile_bytes;      // (32 >> log2P) * pitch
+    int nsw;              // ring stages per warp
+    const uint8_t *query; // device, pitch bytes, zero padded
+    int root;             // metric L2: take the square root
+    int k;                // 0 => no top-k (dist_all only)
+    int kcap;             // k rounded up to 32
+    float *lists;         // [streams][kcap]  k smallest distances of each stream (unsorted, +INF padded)
+    uint2 *logs;          // [streams][logcap] (dist bits, local row)
+    int *counts;          // [streams] log entries written (may exceed logcap => overflow)
+    int logcap;
+    int *ctrl;            // ctrl[1] = overflow flag
+    float *dist_all;      // optional [n]
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// monotone float -> uint32 key (total order, -0 < +0), used for warp-wide max via REDUX
+__device__ __forceinline__ uint32_t fkey(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ------------------------------------------------------------------ accumulation
+struct Accum {
+    float s0, s1;   // fp: primary sum split in two chains (dot / sum of squares / sum of |d|)
+    float ny, nx;   // fp cosine: row norm, query norm (f16 only; others take the query norm once per CTA)
+    int ia, ib;     // int: dot or sad, row norm
+    int flag;       // f16 cosine: an infinity was seen
+};
+
+template <int VT>
+__device__ __forceinline__ void unpack8(const uint4 v, float (&o)[8]) {
+    if constexpr (VT == T_F32) {
+        o[0] = __uint_as_float(v.x); o[1] = __uint_as_float(v.y); o[2] = __uint_as_float(v.z); o[3] = __uint_as_float(v.w);
+    } else if constexpr (VT == T_F16) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __half2 h = *reinterpret_cast<const __half2 *>(&w[j]);
+            float2 f = __half22float2(h);
+            o[2 * j] = f.x; o[2 * j + 1] = f.y;
+        }
+    } else {  // bf16: value = bits << 16 (src/distance-cpu.h:100-102)
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o[2 * j] = __uint_as_float(w[j] << 16);
+            o[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+    }
+}
+
+// one 16-byte chunk of the row (r) against the same chunk of the query (q)
+template <int VT, int MC>
+__device__ __forceinline__ void accum16(Accum &A, const uint4 r, const uint4 q) {
+    if constexpr (VT == T_U8 || VT == T_I8) {
+        const uint32_t rw[4] = {r.x, r.y, r.z, r.w}, qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if constexpr (MC == MC_L1) {
+                // sum |a-b|: per-byte absolute difference, then dot with 1s (exact)
+                uint32_t ad = (VT == T_U8) ? __vabsdiffu4(rw[j], qw[j]) : __vabsdiffs4(rw[j], qw[j]);
+                A.ia = (int)__dp4a(ad, 0x01010101u, (uint32_t)A.ia);
+            } else {
+                if constexpr (VT == T_U8) {
+                    A.ia = (int)__dp4a(rw[j], qw[j], (uint32_t)A.ia);
+                    if constexpr (MC != MC_DOT) A.ib = (int)__dp4a(rw[j], rw[j], (uint32_t)A.ib);
+                } else {
+                    A.ia = __dp4a((int)rw[j], (int)qw[j], A.ia);
+                    if constexpr (MC != MC_DOT) A.ib = __dp4a((int)rw[j], (int)rw[j], A.ib);
+                }
+            }
+        }
+    } else {
+        constexpr int NE = (VT == T_F32) ? 4 : 8;
+        float y[8], x[8];
+        unpack8<VT>(r, y);
+        unpack8<VT>(q, x);
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+            float &s = (j & 1) ? A.s1 : A.s0;
+            // NaN-lane policies of the reference: f16 kernels skip a lane when either INPUT is NaN
+            // (src/distance-cpu.c:338, 383, 413, 444); the bf16 L2 kernel skips a NaN DIFFERENCE (:182).
+            bool skip = false;
+            if constexpr (VT == T_F16) skip = (x[j] != x[j]) || (y[j] != y[j]);
+            if constexpr (MC == MC_L2) {
+                float d = x[j] - y[j];
+                if constexpr (VT == T_BF16) skip = (d != d);
+                if (!skip) s = fmaf(d, d, s);
+            } else if constexpr (MC == MC_L1) {
+                if (!skip) s += fabsf(x[j] - y[j]);
+            } else if constexpr (MC == MC_DOT) {
+                if (!skip) s = fmaf(x[j], y[j], s);
+            } else {  // cosine
+                if (!skip) {
+                    s = fmaf(x[j], y[j], s);
+                    A.ny = fmaf(y[j], y[j], A.ny);
+                    if constexpr (VT == T_F16) {
+                        A.nx = fmaf(x[j], x[j], A.nx);
+                        A.flag |= (isinf(x[j]) || isinf(y[j])) ? 1 : 0;
+                    }
+                }
+            }
+        }
+    }
+}
+
+struct QueryNorm {
+    float f;     // fp: sum x^2 of the query
+    int i;       // int: sum q^2 (bit pattern; unsigned for u8)
+};
+
+// accumulators -> the float the reference kernel returns, then the nearly-zero clamp
+template <int VT, int MC>
+__device__ __forceinline__ float finalize(const Accum &A, const QueryNorm qn, int root) {
+    float d;
+    if constexpr (VT == T_U8 || VT == T_I8) {
+        if constexpr (MC == MC_L2) {
+            // sum (a-b)^2 = |q|^2 + |row|^2 - 2 q.row, exact in 32-bit (src/distance-avx2.c int32 path;
+            // equals the float-accumulating scalar kernel, src/distance-cpu.c:470-502, while sums < 2^24)
+            float f;
+            if constexpr (VT == T_U8) f = (float)((uint32_t)qn.i + (uint32_t)A.ib - 2u * (uint32_t)A.ia);
+            else f = (float)(qn.i + A.ib - 2 * A.ia);
+            d = root ? __fsqrt_rn(f) : f;
+        } else if constexpr (MC == MC_COS) {
+            // src/distance-cpu.c:533-538, 645-650
+            if (qn.i == 0 || A.ib == 0) d = 1.0f;
+            else {
+                float fq = (VT == T_U8) ? (float)(uint32_t)qn.i : (float)qn.i;
+                float fr = (VT == T_U8) ? (float)(uint32_t)A.ib : (float)A.ib;
+                float fd = (VT == T_U8) ? (float)(uint32_t)A.ia : (float)A.ia;
+                float den = __fmul_rn(__fsqrt_rn(fq), __fsqrt_rn(fr));
+                d = __fsub_rn(1.0f, __fdiv_rn(fd, den));
+            }
+        } else if constexpr (MC == MC_DOT) {
+            d = (VT == T_U8) ? -(float)(uint32_t)A.ia : -(float)A.ia;
+        } else {
+            d = (float)(uint32_t)A.ia;
+        }
+    } else {
+        const float s = A.s0 + A.s1;
+        if constexpr (MC == MC_L2) d = root ? __fsqrt_rn(s) : s;
+        else if constexpr (MC == MC_DOT) d = -s;
+        else if constexpr (MC == MC_L1) d = s;
+        else {
+            if constexpr (VT == T_F16) {
+                // src/distance-cpu.c:444-465: any Inf -> 1; bad denominator -> 1; clamp cos to [-1,1]
+                float den = __fmul_rn(__fsqrt_rn(A.nx), __fsqrt_rn(A.ny));
+                if (A.flag || !(den > 0.0f) || isinf(den) || den != den || isinf(s) || s != s) d = 1.0f;
+                else {
+                    float c = __fdiv_rn(s, den);
+                    c = fminf(1.0f, fmaxf(-1.0f, c));
+                    d = 1.0f - c;
+                }
+            } else {
+                // src/distance-cpu.c:105-109, 248-252
+                if (qn.f == 0.0f || A.ny == 0.0f) d = 1.0f;
+                else d = __fsub_rn(1.0f, __fdiv_rn(s, __fmul_rn(__fsqrt_rn(qn.f), __fsqrt_rn(A.ny))));
+            }
+        }
+    }
+    // nearly_zero_float32: |d| <= 8*FLT_EPSILON -> +0.0 (src/sqlite-vector.c:994-996, 2099, 2143)
+    return (fabsf(d) <= 8.0f * FLT_EPSILON) ? 0.0f : d;
+}
+
+__device__ __forceinline__ void accum_reduce(Accum &A, int P) {
+    for (int off = P >> 1; off >= 1; off >>= 1) {
+        A.s0 += __shfl_xor_sync(0xFFFFFFFFu, A.s0, off);
+        A.s1 += __shfl_xor_sync(0xFFFFFFFFu, A.s1, off);
+        A.ny += __shfl_xor_sync(0xFFFFFFFFu, A.ny, off);
+        A.nx += __shfl_xor_sync(0xFFFFFFFFu, A.nx, off);
+        A.ia += __shfl_xor_sync(0xFFFFFFFFu, A.ia, off);
+        A.ib += __shfl_xor_sync(0xFFFFFFFFu, A.ib, off);
+        A.flag |= __shfl_xor_sync(0xFFFFFFFFu, A.flag, off);
+    }
+}
+
+// ------------------------------------------------------------------ warp-private k-smallest list
+// list[0..kcap) in shared memory: entries < k start at +INF, entries >= k at -INF (never the max).
+// Returns the current maximum (= running k-th smallest, +INF until k rows were seen) and its position.
+__device__ __forceinline__ void list_argmax(const float *list, int kcap, int lane, float &thr, int &pos) {
+    float best = list[lane];
+    int bi = lane;
+    for (int j = lane + 32; j < kcap; j += 32) {
+        float v = list[j];
+        if (v > best) { best = v; bi = j; }
+    }
+    uint32_t key = fkey(best);
+    uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, key);
+    int src = __ffs(__ballot_sync(0xFFFFFFFFu, key == mx)) - 1;
+    thr = __shfl_sync(0xFFFFFFFFu, best, src);
+    pos = __shfl_sync(0xFFFFFFFFu, bi, src);
+}
+
+// ------------------------------------------------------------------ the scan kernel
+template <int VT, int MC, bool DIRECT>
+__global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);                    // [kWarps][kMaxStages]
+    QueryNorm *qn_s = reinterpret_cast<QueryNorm *>(smem + kWarps * kMaxStages * 8);
+    uint8_t *qs = smem + kBarrierBytes;                                      // query, pitch bytes
+    float *lists_s = reinterpret_cast<float *>(qs + prm.pitch);              // [kWarps][kcap]
+    const int list_bytes = kWarps * prm.kcap * 4;
+    uint8_t *ring = qs + ((prm.pitch + list_bytes + 127) & ~127);            // [kWarps][nsw][wtile_bytes]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int P = 1 << prm.log2P, rpw = 32 >> prm.log2P;
+    const int nsw = prm.nsw;
+
+    // ---- prologue: barriers, query, query norm
+    if (tid == 0) {
+        for (int i = 0; i < kWarps * kMaxStages; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < prm.nc; i += kThreads)
+        reinterpret_cast<uint4 *>(qs)[i] = reinterpret_cast<const uint4 *>(prm.query)[i];
+    __syncthreads();
+    if (warp == 0) {
+        float f = 0.0f;
+        int iq = 0;
+        for (int c = lane; c < prm.nc; c += 32) {
+            const uint4 q = reinterpret_cast<const uint4 *>(qs)[c];
+            if constexpr (VT == T_U8) {
+                iq = (int)__dp4a(q.x, q.x, (uint32_t)iq); iq = (int)__dp4a(q.y, q.y, (uint32_t)iq);
+                iq = (int)__dp4a(q.z, q.z, (uint32_t)iq); iq = (int)__dp4a(q.w, q.w, (uint32_t)iq);
+            } else if constexpr (VT == T_I8) {
+                iq = __dp4a((int)q.x, (int)q.x, iq); iq = __dp4a((int)q.y, (int)q.y, iq);
+                iq = __dp4a((int)q.z, (int)q.z, iq); iq = __dp4a((int)q.w, (int)q.w, iq);
+            } else {
+                float x[8];
+                unpack8<VT>(q, x);
+                constexpr int NE = (VT == T_F32) ? 4 : 8;
+#pragma unroll
+                for (int j = 0; j < NE; ++j) f = fmaf(x[j], x[j], f);
+            }
+        }
+        for (int off = 16; off >= 1; off >>= 1) {
+            f += __shfl_xor_sync(0xFFFFFFFFu, f, off);
+            iq += __shfl_xor_sync(0xFFFFFFFFu, iq, off);
+        }
+        if (lane == 0) { qn_s->f = f; qn_s->i = iq; }
+    }
+    float *mylist = lists_s + warp * prm.kcap;
+    for (int j = lane; j < prm.kcap; j += 32) mylist[j] = (j < prm.k) ? INFINITY : -INFINITY;
+    __syncthreads();
+    const QueryNorm qn = *qn_s;
+
+    // ---- this warp's stream: a contiguous range of warp-tiles (rpw rows each)
+    const long long S = (long long)gridDim.x * kWarps;
+    const long long sidx = (long long)blockIdx.x * kWarps + warp;
+    const long long T = (prm.n + rpw - 1) / rpw;
+    const long long t0 = (T * sidx) / S, t1 = (T * (sidx + 1)) / S;
+    const int ntiles = (int)(t1 - t0);
+
+    uint64_t *mybars = bars + warp * kMaxStages;
+    uint8_t *myring = ring + (size_t)warp * nsw * prm.wtile_bytes;
+    const uint64_t pol = policy_evict_first();
+
+    auto issue = [&](int it) {  // lane 0 only
+        const long long tile = t0 + it;
+        const long long row0 = tile * rpw;
+        long long rows = prm.n - row0;
+        if (rows > rpw) rows = rpw;
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)prm.pitch;
+        const int s = it % nsw;
+        mbar_expect_tx(&mybars[s], bytes);
+        bulk_g2s(myring + (size_t)s * prm.wtile_bytes, prm.vec + (size_t)row0 * prm.pitch, bytes, &mybars[s], pol);
+    };
+    if constexpr (!DIRECT) {
+        if (lane == 0)
+            for (int it = 0; it < nsw && it < ntiles; ++it) issue(it);
+    }
+
+    const int r = lane >> prm.log2P, p = lane & (P - 1);
+    const int cnt = (prm.nc > p) ? (prm.nc - p + P - 1) >> prm.log2P : 0;  // chunks owned by this lane
+    const int i0 = cnt ? (r % cnt) : 0;                                       // rotation: conflict-free LDS.128
+
+    float thr = INFINITY;
+    int pos = 0, logged = 0;
+    const bool topk = prm.k > 0;
+    uint2 *mylog = prm.logs + (size_t)sidx * prm.logcap;
+
+    for (int it = 0; it < ntiles; ++it) {
+        const long long row0 = (t0 + it) * rpw;
+        const bool valid = (row0 + r) < prm.n;
+        Accum A = {0.f, 0.f, 0.f, 0.f, 0, 0, 0};
+        if constexpr (!DIRECT) {
+            const int s = it % nsw;
+            mbar_wait(&mybars[s], (uint32_t)((it / nsw) & 1));
+            const uint8_t *rowp = myring + (size_t)s * prm.wtile_bytes + (size_t)r * prm.pitch;
+            if (valid) {
+#pragma unroll 4
+                for (int i = 0; i < cnt; ++i) {
+                    int ii = i0 + i;
+                    if (ii >= cnt) ii -= cnt;
+                    const int c = p + (ii << prm.log2P);
+                    const uint4 rv = *reinterpret_cast<const uint4 *>(rowp + (size_t)c * 16);
+                    const uint4 qv = *reinterpret_cast<const uint4 *>(qs + (size_t)c * 16);
+                    accum16<VT, MC>(A, rv, qv);
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && it + nsw < ntiles) issue(it + nsw);
+        } else {
+            const uint8_t *rowp = prm.vec + (size_t)(row0 + r) * prm.pitch;
+            if (valid) {
+#pragma unroll 4
+                for (int i = 0; i < cnt; ++i) {
+                    const int c = p + (i << prm.log2P);
+                    const uint4 rv = ldg_stream(reinterpret_cast<const uint4 *>(rowp) + c);
+                    const uint4 qv = *reinterpret_cast<const uint4 *>(qs + (size_t)c * 16);
+                    accum16<VT, MC>(A, rv, qv);
+                }
+            }
+        }
+        accum_reduce(A, P);
+        const float d = finalize<VT, MC>(A, qn, prm.root);
+        if (prm.dist_all != nullptr && valid && p == 0) prm.dist_all[row0 + r] = d;
+        if (topk) {
+            // rows are visited in scan order (lane order); strict '<' like the reference (:2102, :2145)
+            unsigned m = __ballot_sync(0xFFFFFFFFu, valid && p == 0 && d < thr);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float dv = __shfl_sync(0xFFFFFFFFu, d, src);
+                if (dv < thr) {
+                    if (lane == 0) {
+                        if (logged < prm.logcap) mylog[logged] = make_uint2(__float_as_uint(dv), (uint32_t)(row0 + (src >> prm.log2P)));
+                        mylist[pos] = dv;
+                    }
+                    ++logged;
+                    __syncwarp();
+                    list_argmax(mylist, prm.kcap, lane, thr, pos);
+                }
+            }
+        }
+    }
+    if (topk) {
+        __syncwarp();
+        float *gl = prm.lists + (size_t)sidx * prm.kcap;
+        for (int j = lane; j < prm.kcap; j += 32) gl[j] = mylist[j];
+        if (lane == 0) {
+            prm.counts[sidx] = logged;
+            if (logged > prm.logcap) atomicExch(&prm.ctrl[1], 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ candidate filter
+// One warp per stream.  thresholds: a row of stream s can only enter the reference's slots if its distance
+// is below the k-th smallest distance among ALL earlier rows; any subset of earlier rows gives a valid upper
+// bound.  We use  min( k-th smallest over all streams of earlier segments,
+//                      k-th smallest over the earlier streams of the same segment ),
+// both built from the streams' final k-lists (each contains the k smallest values of its stream).
+struct FilterParams {
+    int S;              // streams
+    int k, kcap;
+    const float *lists; // [S][kcap]
+    const uint2 *logs;  // [S][logcap]
+    const int *counts;  // [S]
+    int logcap;
+    uint2 *out;         // survivors (dist bits, local row), grouped by block in stream order
+    int outcap;
+    int2 *table;        // [gridDim.x] (base, count) of each block's survivors in out
+    int *hdr;           // hdr[0] = total survivors, hdr[1] = overflow flag, hdr[2] = sequence number
+    int *ctrl;          // device: [0] cursor, [1] overflow from scan_kernel, [2] blocks done
+    int seqno;
+};
+
+constexpr int kFilterWarps = 32;
+
+__global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const FilterParams fp) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    float *seglist = reinterpret_cast<float *>(fsm);                        // [32][kcap] k smallest of each segment
+    float *work = seglist + kFilterWarps * fp.kcap;                         // [32][kcap] scratch list per warp
+    float *tlocal = work + kFilterWarps * fp.kcap;                          // [S] in-segment prefix threshold
+    float *tseg = tlocal + fp.S;                                            // [32]
+    __shared__ int wcount[kFilterWarps], woff[kFilterWarps];
+    __shared__ int blk_base;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = (fp.S + kFilterWarps - 1) / kFilterWarps;                 // streams per segment
+    const int k = fp.k, kcap = fp.kcap;
+
+    // phase 1: warp g walks segment g in stream order, recording the running k-th value before each stream
+    {
+        float *L = seglist + warp * kcap;
+        for (int j = lane; j < kcap; j += 32) L[j] = (j < k) ? INFINITY : -INFINITY;
+        __syncwarp();
+        float thr = INFINITY;
+        int pos = 0;
+        const int s0 = warp * G, s1 = min(fp.S, s0 + G);
+        for (int s = s0; s < s1; ++s) {
+            if (lane == 0) tlocal[s] = thr;
+            const float *src = fp.lists + (size_t)s * kcap;
+            for (int base = 0; base < k; base += 32) {
+                const int j = base + lane;
+                const float v = (j < k) ? src[j] : INFINITY;
+                unsigned m = __ballot_sync(0xFFFFFFFFu, v < thr);
+                while (m) {
+                    const int sl = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float dv = __shfl_sync(0xFFFFFFFFu, v, sl);
+                    if (dv < thr) {
+                        if (lane == 0) L[pos] = dv;
+                        __syncwarp();
+                        list_argmax(L, kcap, lane, thr, pos);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // phase 2: warp g merges the lists of segments 0..g-1 -> threshold valid for every stream of segment g
+    {
+        float *L = work + warp * kcap;
+        for (int j = lane; j < kcap; j += 32) L[j] = (j < k) ? INFINITY : -INFINITY;
+        __syncwarp();
+        float thr = INFINITY;
+        int pos = 0;
+        for (int g = 0; g < warp; ++g) {
+            const float *src = seglist + g * kcap;
+            for (int base = 0; base < k; base += 32) {
+                const int j = base + lane;
+                const float v = (j < k) ? src[j] : INFINITY;
+                unsigned m = __ballot_sync(0xFFFFFFFFu, v < thr);
+                while (m) {
+                    const int sl = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float dv = __shfl_sync(0xFFFFFFFFu, v, sl);
+                    if (dv < thr) {
+                        if (lane == 0) L[pos] = dv;
+                        __syncwarp();
+                        list_argmax(L, kcap, lane, thr, pos);
+                    }
+                }
+            }
+        }
+        if (lane == 0) tseg[warp] = thr;
+    }
+    __syncthreads();
+
+    // phase 3: count, reserve, write — survivors of this block's 32 streams in stream order
+    const int s = blockIdx.x * kFilterWarps + warp;
+    int n_log = 0;
+    float T = INFINITY;
+    if (s < fp.S) {
+        n_log = min(fp.counts[s], fp.logcap);
+        T = fminf(tlocal[s], tseg[s / G]);
+    }
+    const uint2 *lg = fp.logs + (size_t)s * fp.logcap;
+    int mine = 0;
+    for (int base = 0; base < n_log; base += 32) {
+        const int j = base + lane;
+        const bool keep = (j < n_log) && (__uint_as_float(lg[j].x) < T);
+        mine += __popc(__ballot_sync(0xFFFFFFFFu, keep));
+    }
+    if (lane == 0) wcount[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < kFilterWarps; ++w) { woff[w] = tot; tot += wcount[w]; }
+        const int base = atomicAdd(&fp.ctrl[0], tot);
+        blk_base = base;
+        fp.table[blockIdx.x] = make_int2(base, tot);
+    }
+    __syncthreads();
+    int wr = blk_base + woff[warp];
+    for (int base = 0; base < n_log; base += 32) {
+        const int j = base + lane;
+        uint2 e = make_uint2(0, 0);
+        bool keep = false;
+        if (j < n_log) { e = lg[j]; keep = __uint_as_float(e.x) < T; }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+        const int off = wr + __popc(m & ((1u << lane) - 1u));
+        if (keep && off < fp.outcap) fp.out[off] = e;
+        wr += __popc(m);
+    }
+    // last block publishes the header and re-arms the control words for the next query
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(&fp.ctrl[2], 1);
+        if (done == (int)gridDim.x - 1) {
+            const int total = atomicAdd(&fp.ctrl[0], 0);
+            const int ovf = atomicAdd(&fp.ctrl[1], 0);
+            fp.hdr[0] = total;
+            fp.hdr[1] = (ovf != 0 || total > fp.outcap) ? 1 : 0;
+            __threadfence_system();
+            fp.hdr[2] = fp.seqno;
+            fp.ctrl[0] = 0; fp.ctrl[1] = 0; fp.ctrl[2] = 0;
+        }
+    }
+}
+
+}  // namespace vsb

@@ -1,0 +1,222 @@
+"""CUDA path vs the oracle through the C ABI (include/vsb200.h).  Run on the B200 box: pytest -m gpu.
+
+Bit-exact for int8/uint8 (rowids, order, distances); 1e-5 relative for fp distances
+(tolerance relative to max(|d|, sum|a_i*b_i| scale) as documented in DESIGN.md §5)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+TYPES = [po.F32, po.F16, po.BF16, po.U8, po.I8]
+METRICS = [po.L2, po.L2SQ, po.COS, po.DOT, po.L1]
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import sqlite_vector_b200 as vs
+    e = vs.load_engine()
+    assert e.device_count() >= 1, "no CUDA device: the GPU tests must not pass on a fallback"
+    return e
+
+
+def make_index(vtype, x, rowids=None, **kw):
+    import sqlite_vector_b200 as vs
+    ix = vs.Index(vtype, x.shape[1], x.shape[0], **kw)
+    ix.append_dense(x, rowids)
+    ix.finalize()
+    return ix
+
+
+def fp_tol(oracle, metric, vtype, q, x, ids_rows):
+    """absolute tolerance per row: 1e-5 * max(|d|, magnitude of the terms being summed)"""
+    return 1e-5
+
+
+def check_fp(oracle, metric, vtype, q, x, got_ids, got_d, k, rowids):
+    want_ids, want_d = oracle.scan_dense(metric, vtype, q, x, rowids, k)
+    assert len(got_ids) == len(want_ids)
+    # distances (sorted ascending on both sides) agree to 1e-5 relative (+ tiny abs for cancellation-prone metrics)
+    xf = None
+    scale = np.maximum(np.abs(want_d), 1e-30)
+    if metric in (po.DOT, po.COS):
+        scale = np.maximum(scale, 1.0 if metric == po.COS else float(np.abs(want_d).max()))
+    assert np.all(np.abs(got_d - want_d) <= 1e-5 * scale + 1e-30), (metric, vtype, np.abs(got_d - want_d).max())
+    # same rows except where the oracle's own distances are within tolerance of each other (near ties)
+    if not np.array_equal(got_ids, want_ids):
+        dall = oracle.distances_all(metric, vtype, q, x).astype(np.float64)
+        pos = {int(r): i for i, r in enumerate(rowids)}
+        kth = want_d[-1]
+        for r in set(got_ids.tolist()) ^ set(want_ids.tolist()):
+            assert abs(dall[pos[int(r)]] - kth) <= 2e-5 * max(abs(kth), 1e-30 if metric not in (po.DOT, po.COS) else scale.max()), (metric, vtype, r)
+
+
+@pytest.mark.parametrize("vtype", TYPES)
+@pytest.mark.parametrize("metric", METRICS)
+def test_all_distances_match_oracle(eng, oracle, vtype, metric):
+    rng = np.random.Generator(np.random.PCG64(1000 + 10 * vtype + metric))
+    for (n, dim) in [(1000, 128), (777, 384), (300, 771), (64, 1536), (2050, 5)]:
+        x = po.convert(rng.standard_normal((n, dim), dtype=np.float32), vtype)
+        q = po.convert(rng.standard_normal((1, dim), dtype=np.float32), vtype)[0]
+        ix = make_index(vtype, x)
+        got = ix.scan_all(metric, q)
+        want = oracle.distances_all(metric, vtype, q, x, int_exact=True)
+        if vtype in (po.U8, po.I8):
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (vtype, metric, n, dim)
+            want_scalar = oracle.distances_all(metric, vtype, q, x, int_exact=False)  # distance-cpu.c float accumulation
+            assert np.array_equal(got.view(np.uint32), want_scalar.view(np.uint32)), "sums < 2^24 here: scalar == exact"
+        else:
+            scale = np.maximum(np.abs(want), 1e-30)
+            if metric == po.COS:
+                scale = np.maximum(scale, 1.0)
+            if metric == po.DOT:
+                xf = oracle.distances_all(po.L1, vtype, np.zeros_like(q), x)  # sum |x_i| as magnitude proxy
+                scale = np.maximum(scale, 1e-2 * xf)
+            assert np.all(np.abs(got - want) <= 1e-5 * scale), (vtype, metric, n, dim, np.max(np.abs(got - want) / scale))
+        ix.close()
+
+
+@pytest.mark.parametrize("vtype", [po.U8, po.I8])
+@pytest.mark.parametrize("metric", METRICS)
+def test_topk_int_bit_exact_with_ties(eng, oracle, vtype, metric):
+    rng = np.random.Generator(np.random.PCG64(2000 + 10 * vtype + metric))
+    for (n, dim, k, spread) in [(5000, 16, 20, 3), (20000, 32, 20, 30), (50, 8, 100, 2), (3000, 4, 7, 1), (40000, 384, 33, 60), (9, 16, 20, 5)]:
+        lo, hi = (0, 2 * spread) if vtype == po.U8 else (-spread, spread)
+        x = rng.integers(lo, hi + 1, (n, dim)).astype(po.NP_STORAGE[vtype])
+        rowids = np.arange(n, dtype=np.int64) * 3 + 7
+        q = rng.integers(lo, hi + 1, dim).astype(x.dtype)
+        ix = make_index(vtype, x, rowids)
+        for smi in (0, min(2, k - 1)):
+            (res,), mi = ix.scan_topk(metric, q, k, max_index=smi)
+            want_ids, want_d = oracle.scan_dense(metric, vtype, q, x, rowids, k, start_max_index=smi)
+            assert np.array_equal(res[0], want_ids), (vtype, metric, n, dim, k)
+            assert np.array_equal(res[1], want_d)
+        ix.close()
+
+
+@pytest.mark.parametrize("vtype", [po.F32, po.F16, po.BF16])
+@pytest.mark.parametrize("metric", METRICS)
+def test_topk_fp(eng, oracle, vtype, metric):
+    rng = np.random.Generator(np.random.PCG64(3000 + 10 * vtype + metric))
+    for (n, dim, k) in [(20000, 128, 20), (5000, 384, 20), (3000, 768, 50), (100, 24, 200)]:
+        x = po.convert(rng.standard_normal((n, dim), dtype=np.float32), vtype)
+        q = po.convert(rng.standard_normal((1, dim), dtype=np.float32), vtype)[0]
+        rowids = np.arange(1, n + 1, dtype=np.int64)
+        ix = make_index(vtype, x, rowids)
+        (res,) = ix.scan_topk(metric, q, k)
+        check_fp(oracle, metric, vtype, q, x, res[0], res[1], k, rowids)
+        ix.close()
+
+
+def test_quant_chunk_preload_layout(eng, oracle):
+    """vsb_index_append_quant_chunk consumes the reference's shadow-table blob format."""
+    rng = np.random.Generator(np.random.PCG64(42))
+    n, dim, k = 30000, 384, 20
+    xf = rng.standard_normal((n, dim), dtype=np.float32)
+    scale, offset, qt = oracle.quant_params(po.F32, xf)
+    assert qt == po.Q_S8
+    rowids = np.arange(n, dtype=np.int64) * 2 + 1
+    buf = oracle.build_quant_buffer(po.F32, xf, rowids, offset, scale, qt)
+    import sqlite_vector_b200 as vs
+    ix = vs.Index(po.I8, dim, n)
+    third = (n // 3) * (8 + dim)
+    ix.append_quant_chunk(buf[:third], n // 3)            # chunked like the 30 MB shadow-table rows
+    ix.append_quant_chunk(buf[third:], n - n // 3)
+    ix.finalize()
+    qf = rng.standard_normal(dim).astype(np.float32)
+    qq = oracle.quantize(po.F32, qf, offset, scale, qt)
+    for metric in METRICS:
+        (res,) = ix.scan_topk(metric, qq, k)
+        want_ids, want_d = oracle.scan_quant_buffer(metric, qt, qq, buf, n, dim, k)
+        assert np.array_equal(res[0], want_ids) and np.array_equal(res[1], want_d), metric
+    ix.close()
+
+
+def test_golden_topk(eng):
+    """CUDA vs the committed reference outputs (no oracle in the loop)."""
+    g = np.load(os.path.join(G, "topk.npz"))
+    for c in range(int(g["ncases"][0])):
+        qt, n, dim, k = (int(v) for v in g[f"c{c}_meta"])
+        vt = po.U8 if qt == po.Q_U8 else po.I8
+        ix = make_index(vt, g[f"c{c}_vec"], g[f"c{c}_rowids"])
+        for m in METRICS:
+            (res,) = ix.scan_topk(m, g[f"c{c}_q"], k)
+            assert np.array_equal(res[0], g[f"c{c}_ids_{m}"]) and np.array_equal(res[1], g[f"c{c}_dist_{m}"]), (c, m)
+        ix.close()
+
+
+def test_edge_cases(eng, oracle):
+    rng = np.random.Generator(np.random.PCG64(9))
+    x = rng.integers(-5, 6, (100, 16)).astype(np.int8)
+    ix = make_index(po.I8, x)
+    q = x[3].copy()
+    (res,) = ix.scan_topk(po.L2, q, 0)                     # k = 0 -> empty (sqlite-vector.c:1796)
+    assert len(res[0]) == 0
+    (res,) = ix.scan_topk(po.L2, q, 150)                   # k > n -> n rows, INF slots trimmed
+    want_ids, want_d = oracle.scan_dense(po.L2, po.I8, q, x, np.arange(1, 101, dtype=np.int64), 150)
+    assert np.array_equal(res[0], want_ids) and np.array_equal(res[1], want_d)
+    (res,) = ix.scan_topk(po.L2, q, 300)                   # k above the candidate path -> all-distances path
+    want_ids, want_d = oracle.scan_dense(po.L2, po.I8, q, x, np.arange(1, 101, dtype=np.int64), 300)
+    assert np.array_equal(res[0], want_ids) and np.array_equal(res[1], want_d)
+    ix.close()
+    # descending distances: every row enters the slots -> candidate log overflows -> exact fallback
+    n = 200000
+    x = np.zeros((n, 16), dtype=np.int8)
+    x[:, 0] = np.clip(np.arange(n)[::-1] // 1600, 0, 127)
+    ix = make_index(po.I8, x)
+    q = np.zeros(16, dtype=np.int8)
+    (res,) = ix.scan_topk(po.L1, q, 20)
+    want_ids, want_d = oracle.scan_dense(po.L1, po.I8, q, x, np.arange(1, n + 1, dtype=np.int64), 20)
+    assert np.array_equal(res[0], want_ids) and np.array_equal(res[1], want_d)
+    ix.close()
+    # empty index
+    import sqlite_vector_b200 as vs
+    ix = vs.Index(po.F32, 8, 0)
+    ix.finalize()
+    (res,) = ix.scan_topk(po.L2, np.zeros(8, np.float32), 5)
+    assert len(res[0]) == 0
+    ix.close()
+
+
+def test_special_values_f16(eng, oracle):
+    """NaN lanes are skipped and a single infinity propagates like the reference (distance-cpu.c:318-466)."""
+    x = po.convert(np.random.Generator(np.random.PCG64(5)).standard_normal((64, 8), dtype=np.float32), po.F16)
+    x[3, 2] = 0x7E00   # NaN
+    x[5, 1] = 0x7C00   # +Inf
+    x[9, :] = 0        # zero vector
+    q = x[0].copy()
+    ix = make_index(po.F16, x)
+    for metric in METRICS:
+        got = ix.scan_all(metric, q)
+        want = oracle.distances_all(metric, po.F16, q, x)
+        both_nan = np.isnan(got) & np.isnan(want)
+        ok = both_nan | (np.abs(got - want) <= 1e-5 * np.maximum(np.abs(want), 1.0)) | (got == want)
+        assert ok.all(), (metric, got[~ok], want[~ok])
+    ix.close()
+
+
+def test_multi_shard_candidates_replay(eng, oracle):
+    """row-sharded scan: per-shard candidates concatenated in scan order + vsb_replay_topk == one-shard result."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    n, dim, k = 60000, 64, 20
+    x = rng.integers(-20, 21, (n, dim)).astype(np.int8)
+    q = rng.integers(-20, 21, dim).astype(np.int8)
+    rowids = np.arange(1, n + 1, dtype=np.int64)
+    import sqlite_vector_b200 as vs
+    bounds = [0, 15000, 15001, 40000, n]
+    parts = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        ix = vs.Index(po.I8, dim, b - a, first_seq=a)
+        ix.append_dense(x[a:b], rowids[a:b])
+        ix.finalize()
+        parts.append(ix.scan_candidates(po.L2, q, k)[0])
+        ix.close()
+    cands = np.concatenate(parts)
+    assert np.all(np.diff(cands["seq"]) > 0)
+    ids, d, _ = eng.replay_topk(cands, k)
+    want_ids, want_d = oracle.scan_dense(po.L2, po.I8, q, x, rowids, k)
+    assert np.array_equal(ids, want_ids) and np.array_equal(d, want_d)
