@@ -46,8 +46,10 @@ _SIGNATURES = {
     "vsb_collect_last": (_i, [_vp, _i, _vp, _vp, _vp]),
     "vsb_index_query_pitch": (_i, [_vp]),
     "vsb_index_stream": (_vp, [_vp]),
+    "vsb_index_stat": (_i64, [_vp, C.c_char_p]),
     "vsb_kernel_launches": (_i64, []),
     "vsb_set_option": (_i, [C.c_char_p, _i]),
+    "vsb_profile_read": (_i, [_vp, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -183,6 +185,15 @@ class Index:
 
     def scan_device_query(self, metric: int, d_query_ptr: int, k: int):
         self.eng.check(self.eng.lib.vsb_scan_device_query(self.h, metric, d_query_ptr, k))
+
+    def stat(self, name: str) -> int:
+        return int(self.eng.lib.vsb_index_stat(self.h, name.encode()))
+
+    def profile_read(self):
+        a, b = C.c_double(), C.c_double()
+        na, nb = C.c_int(), C.c_int()
+        self.eng.check(self.eng.lib.vsb_profile_read(self.h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
+        return {"scan_ms": a.value, "scan_launches": na.value, "filter_ms": b.value, "filter_launches": nb.value}
 
     def collect_last(self, k: int):
         ids = np.zeros(max(k, 1), dtype=np.int64)

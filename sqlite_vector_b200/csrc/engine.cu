@@ -32,6 +32,7 @@ std::atomic<long long> g_launches{0};
 int g_opt_stage_bytes = 8192;  // target bytes of one warp tile (ring stage)
 int g_opt_direct = 0;          // 1: force the no-staging kernel
 int g_opt_ring_bytes = 0;      // 0: use all shared memory left
+int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -97,7 +98,12 @@ struct vsb_index {
     bool slots_ready = false;
     float *d_dist_all = nullptr;
     int last_slot = -1, last_metric = 0;
+    // optional per-kernel event timing (vsb_profile_read)
+    std::vector<cudaEvent_t> prof_ev;   // triples: before scan, after scan, after filter
+    std::vector<int> prof_kind;         // 1 = scan only, 2 = scan + filter
+    size_t prof_used = 0;
     size_t dev_bytes = 0;
+    long long st_queries = 0, st_survivors = 0, st_fallbacks = 0, st_last_survivors = 0;
 };
 
 namespace {
@@ -235,9 +241,24 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
     p.logcap = ix->ws_logcap;
     p.ctrl = slot ? slot->d_ctrl : nullptr;
     p.dist_all = d_dist_all;
+    cudaEvent_t *pev = nullptr;
+    if (g_opt_time_kernels) {
+        if (ix->prof_used + 3 > ix->prof_ev.size()) {
+            for (int i = 0; i < 3; ++i) {
+                cudaEvent_t e;
+                CU(cudaEventCreate(&e));
+                ix->prof_ev.push_back(e);
+            }
+        }
+        pev = &ix->prof_ev[ix->prof_used];
+        ix->prof_used += 3;
+        ix->prof_kind.push_back(k > 0 ? 2 : 1);
+        CU(cudaEventRecord(pev[0], ix->stream));
+    }
     fn<<<ix->num_sms, kThreads, pl.smem, ix->stream>>>(p);
     CU(cudaGetLastError());
     ++g_launches;
+    if (pev) CU(cudaEventRecord(pev[1], ix->stream));
     if (k > 0) {
         FilterParams f{};
         f.S = ix->ws_streams;
@@ -255,11 +276,19 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         f.seqno = ++slot->seq;
         const int nblocks = (f.S + kFilterWarps - 1) / kFilterWarps;
         slot->nblocks = nblocks;
-        const size_t fsm = sizeof(float) * ((size_t)2 * kFilterWarps * kcap + (size_t)f.S + 32);
-        CU(cudaFuncSetAttribute((const void *)filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-        filter_kernel<<<nblocks, kFilterWarps * 32, fsm, ix->stream>>>(f);
+        const size_t fsm_base = sizeof(float) * ((size_t)2 * kFilterWarps * kcap + (size_t)f.S + 32);
+        const size_t fsm_fast = fsm_base + sizeof(float) * (size_t)f.S * k;
+        const bool fast = (k <= 32) && fsm_fast + 2048 <= (size_t)ix->max_smem;
+        if (fast) {
+            CU(cudaFuncSetAttribute((const void *)filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm_fast));
+            filter_kernel<true><<<nblocks, kFilterWarps * 32, fsm_fast, ix->stream>>>(f);
+        } else {
+            CU(cudaFuncSetAttribute((const void *)filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm_base));
+            filter_kernel<false><<<nblocks, kFilterWarps * 32, fsm_base, ix->stream>>>(f);
+        }
         CU(cudaGetLastError());
         ++g_launches;
+        if (pev) CU(cudaEventRecord(pev[2], ix->stream));
     }
     return VSB_OK;
 }
@@ -315,7 +344,9 @@ int gather_survivors(vsb_index *ix, Slot *slot, std::vector<uint2> &out, bool *o
         const int2 t = slot->h_table[b];
         for (int i = 0; i < t.y; ++i) out.push_back(slot->h_out[t.x + i]);
     }
-    (void)ix;
+    ix->st_queries++;
+    ix->st_survivors += (long long)out.size();
+    ix->st_last_survivors = (long long)out.size();
     return (int)out.size();
 }
 
@@ -360,6 +391,7 @@ int query_candidates(vsb_index *ix, int metric, const void *query, int k, std::v
         if (n < 0) return n;
     }
     if (overflow) {
+        ix->st_fallbacks++;
         std::vector<float> dist;
         rc = scan_all_into(ix, metric, slot->d_query, dist);
         if (rc) return rc;
@@ -411,6 +443,7 @@ int vsb_set_option(const char *name, int value) {
     if (!strcmp(name, "stage_bytes")) p = &g_opt_stage_bytes;
     else if (!strcmp(name, "direct")) p = &g_opt_direct;
     else if (!strcmp(name, "ring_bytes")) p = &g_opt_ring_bytes;
+    else if (!strcmp(name, "time_kernels")) p = &g_opt_time_kernels;
     if (!p) return fail(VSB_EINVAL, "unknown option %s", name);
     int old = *p;
     *p = value;
@@ -564,6 +597,15 @@ int vsb_index_finalize(vsb_index *ix) {
 int64_t vsb_index_rows(const vsb_index *ix) { return ix ? ix->n : 0; }
 int64_t vsb_index_device_bytes(const vsb_index *ix) { return ix ? (int64_t)ix->dev_bytes : 0; }
 int vsb_index_query_pitch(const vsb_index *ix) { return ix ? ix->pitch : 0; }
+int64_t vsb_index_stat(const vsb_index *ix, const char *name) {
+    if (!ix || !name) return -1;
+    if (!strcmp(name, "queries")) return ix->st_queries;
+    if (!strcmp(name, "survivors")) return ix->st_survivors;
+    if (!strcmp(name, "last_survivors")) return ix->st_last_survivors;
+    if (!strcmp(name, "fallbacks")) return ix->st_fallbacks;
+    if (!strcmp(name, "filter_blocks")) return (ix->num_sms * kWarps + kFilterWarps - 1) / kFilterWarps;
+    return -1;
+}
 void *vsb_index_stream(vsb_index *ix) { return ix ? (void *)ix->stream : nullptr; }
 
 void vsb_index_free(vsb_index *ix) {
@@ -588,6 +630,7 @@ void vsb_index_free(vsb_index *ix) {
     if (ix->d_counts) cudaFree(ix->d_counts);
     if (ix->d_dist_all) cudaFree(ix->d_dist_all);
     if (ix->d_vec) cudaFree(ix->d_vec);
+    for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -674,6 +717,30 @@ int vsb_replay_topk(const vsb_candidate *cands, int n, int k, int *max_index, in
     for (int i = 0; i < n; ++i) slots_offer(s, cands[i].dist, cands[i].rowid);
     if (max_index) *max_index = s.mi;
     return slots_finish(s);
+}
+
+int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double *filter_ms, int *filter_launches) {
+    if (check_index(ix)) return VSB_EINVAL;
+    CU(cudaSetDevice(ix->device));
+    CU(cudaStreamSynchronize(ix->stream));
+    double a = 0, b = 0;
+    int na = 0, nb = 0;
+    for (size_t i = 0; i < ix->prof_kind.size(); ++i) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ix->prof_ev[3 * i], ix->prof_ev[3 * i + 1]));
+        a += ms; ++na;
+        if (ix->prof_kind[i] == 2) {
+            CU(cudaEventElapsedTime(&ms, ix->prof_ev[3 * i + 1], ix->prof_ev[3 * i + 2]));
+            b += ms; ++nb;
+        }
+    }
+    ix->prof_kind.clear();
+    ix->prof_used = 0;
+    if (scan_ms) *scan_ms = a;
+    if (scan_launches) *scan_launches = na;
+    if (filter_ms) *filter_ms = b;
+    if (filter_launches) *filter_launches = nb;
+    return VSB_OK;
 }
 
 int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k) {

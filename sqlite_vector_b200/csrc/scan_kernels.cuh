@@ -446,89 +446,156 @@ struct FilterParams {
 };
 
 constexpr int kFilterWarps = 32;
+constexpr int kLogRegs = 8;   // log entries per lane prefetched into registers (256 per stream)
 
+__device__ __forceinline__ float funkey(uint32_t k) {  // inverse of fkey
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+// k <= 32: the warp's k-list lives in one register per lane (lanes >= k hold -INF and never win the max)
+struct RegList {
+    float v, thr;
+    int pos;
+    __device__ __forceinline__ void init(int lane, int k) { v = (lane < k) ? INFINITY : -INFINITY; thr = INFINITY; pos = 0; }
+    __device__ __forceinline__ void insert(int lane, float dv) {
+        if (lane == pos) v = dv;
+        const uint32_t key = fkey(v);
+        const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, key);
+        pos = __ffs(__ballot_sync(0xFFFFFFFFu, key == mx)) - 1;
+        thr = funkey(mx);
+    }
+    // offer the (<= 32) values held one per lane, in lane order
+    __device__ __forceinline__ void offer(int lane, float val) {
+        unsigned m = __ballot_sync(0xFFFFFFFFu, val < thr);
+        while (m) {
+            const int sl = __ffs(m) - 1;
+            m &= m - 1;
+            const float dv = __shfl_sync(0xFFFFFFFFu, val, sl);
+            if (dv < thr) insert(lane, dv);
+        }
+    }
+};
+
+// FAST: k <= 32 and all S*k list values fit in shared memory (register lists, one L2 round trip).
+template <bool FAST>
 __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const FilterParams fp) {
     extern __shared__ __align__(16) uint8_t fsm[];
+    const int k = fp.k, kcap = fp.kcap;
     float *seglist = reinterpret_cast<float *>(fsm);                        // [32][kcap] k smallest of each segment
-    float *work = seglist + kFilterWarps * fp.kcap;                         // [32][kcap] scratch list per warp
-    float *tlocal = work + kFilterWarps * fp.kcap;                          // [S] in-segment prefix threshold
+    float *work = seglist + kFilterWarps * kcap;                            // [32][kcap] scratch (generic path)
+    float *tlocal = work + kFilterWarps * kcap;                             // [S] in-segment prefix threshold
     float *tseg = tlocal + fp.S;                                            // [32]
+    float *slists = tseg + 32;                                              // FAST: [S][k] copy of all stream lists
     __shared__ int wcount[kFilterWarps], woff[kFilterWarps];
     __shared__ int blk_base;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = (fp.S + kFilterWarps - 1) / kFilterWarps;                 // streams per segment
-    const int k = fp.k, kcap = fp.kcap;
 
-    // phase 1: warp g walks segment g in stream order, recording the running k-th value before each stream
-    {
-        float *L = seglist + warp * kcap;
-        for (int j = lane; j < kcap; j += 32) L[j] = (j < k) ? INFINITY : -INFINITY;
-        __syncwarp();
-        float thr = INFINITY;
-        int pos = 0;
-        const int s0 = warp * G, s1 = min(fp.S, s0 + G);
-        for (int s = s0; s < s1; ++s) {
-            if (lane == 0) tlocal[s] = thr;
-            const float *src = fp.lists + (size_t)s * kcap;
-            for (int base = 0; base < k; base += 32) {
-                const int j = base + lane;
-                const float v = (j < k) ? src[j] : INFINITY;
-                unsigned m = __ballot_sync(0xFFFFFFFFu, v < thr);
-                while (m) {
-                    const int sl = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float dv = __shfl_sync(0xFFFFFFFFu, v, sl);
-                    if (dv < thr) {
-                        if (lane == 0) L[pos] = dv;
-                        __syncwarp();
-                        list_argmax(L, kcap, lane, thr, pos);
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // phase 2: warp g merges the lists of segments 0..g-1 -> threshold valid for every stream of segment g
-    {
-        float *L = work + warp * kcap;
-        for (int j = lane; j < kcap; j += 32) L[j] = (j < k) ? INFINITY : -INFINITY;
-        __syncwarp();
-        float thr = INFINITY;
-        int pos = 0;
-        for (int g = 0; g < warp; ++g) {
-            const float *src = seglist + g * kcap;
-            for (int base = 0; base < k; base += 32) {
-                const int j = base + lane;
-                const float v = (j < k) ? src[j] : INFINITY;
-                unsigned m = __ballot_sync(0xFFFFFFFFu, v < thr);
-                while (m) {
-                    const int sl = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float dv = __shfl_sync(0xFFFFFFFFu, v, sl);
-                    if (dv < thr) {
-                        if (lane == 0) L[pos] = dv;
-                        __syncwarp();
-                        list_argmax(L, kcap, lane, thr, pos);
-                    }
-                }
-            }
-        }
-        if (lane == 0) tseg[warp] = thr;
-    }
-    __syncthreads();
-
-    // phase 3: count, reserve, write — survivors of this block's 32 streams in stream order
+    // ---- issue this warp's log loads first: they do not depend on the thresholds
     const int s = blockIdx.x * kFilterWarps + warp;
     int n_log = 0;
-    float T = INFINITY;
-    if (s < fp.S) {
-        n_log = min(fp.counts[s], fp.logcap);
-        T = fminf(tlocal[s], tseg[s / G]);
-    }
+    uint2 ereg[kLogRegs];
     const uint2 *lg = fp.logs + (size_t)s * fp.logcap;
+    if (s < fp.S) n_log = min(fp.counts[s], fp.logcap);
+#pragma unroll
+    for (int i = 0; i < kLogRegs; ++i) {
+        const int j = i * 32 + lane;
+        ereg[i] = (j < n_log) ? lg[j] : make_uint2(0x7FC00000u, 0u);       // NaN never survives
+    }
+
+    if constexpr (FAST) {
+        // all stream lists -> shared memory, fully parallel and coalesced
+        const int total = fp.S * k;
+        for (int i = threadIdx.x; i < total; i += kFilterWarps * 32) {
+            const int st = i / k, j = i - st * k;
+            slists[i] = fp.lists[(size_t)st * kcap + j];
+        }
+        __syncthreads();
+        {   // phase 1: warp g walks segment g in stream order, recording the running k-th value before each stream
+            RegList L;
+            L.init(lane, k);
+            const int s0 = warp * G, s1 = min(fp.S, s0 + G);
+            for (int st = s0; st < s1; ++st) {
+                if (lane == 0) tlocal[st] = L.thr;
+                L.offer(lane, (lane < k) ? slists[st * k + lane] : INFINITY);
+            }
+            seglist[warp * kcap + lane] = L.v;
+        }
+        __syncthreads();
+        {   // phase 2: warp g merges the lists of segments 0..g-1
+            RegList L;
+            L.init(lane, k);
+            for (int g = 0; g < warp; ++g) L.offer(lane, (lane < k) ? seglist[g * kcap + lane] : INFINITY);
+            if (lane == 0) tseg[warp] = L.thr;
+        }
+        __syncthreads();
+    } else {
+        // generic path (any k): lists stay in global memory / L2, k-lists in shared memory
+        {
+            float *L = seglist + warp * kcap;
+            for (int j = lane; j < kcap; j += 32) L[j] = (j < k) ? INFINITY : -INFINITY;
+            __syncwarp();
+            float thr = INFINITY;
+            int pos = 0;
+            const int s0 = warp * G, s1 = min(fp.S, s0 + G);
+            for (int st = s0; st < s1; ++st) {
+                if (lane == 0) tlocal[st] = thr;
+                const float *src = fp.lists + (size_t)st * kcap;
+                for (int base = 0; base < k; base += 32) {
+                    const int j = base + lane;
+                    const float v = (j < k) ? src[j] : INFINITY;
+                    unsigned m = __ballot_sync(0xFFFFFFFFu, v < thr);
+                    while (m) {
+                        const int sl = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float dv = __shfl_sync(0xFFFFFFFFu, v, sl);
+                        if (dv < thr) {
+                            if (lane == 0) L[pos] = dv;
+                            __syncwarp();
+                            list_argmax(L, kcap, lane, thr, pos);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            float *L = work + warp * kcap;
+            for (int j = lane; j < kcap; j += 32) L[j] = (j < k) ? INFINITY : -INFINITY;
+            __syncwarp();
+            float thr = INFINITY;
+            int pos = 0;
+            for (int g = 0; g < warp; ++g) {
+                const float *src = seglist + g * kcap;
+                for (int base = 0; base < k; base += 32) {
+                    const int j = base + lane;
+                    const float v = (j < k) ? src[j] : INFINITY;
+                    unsigned m = __ballot_sync(0xFFFFFFFFu, v < thr);
+                    while (m) {
+                        const int sl = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float dv = __shfl_sync(0xFFFFFFFFu, v, sl);
+                        if (dv < thr) {
+                            if (lane == 0) L[pos] = dv;
+                            __syncwarp();
+                            list_argmax(L, kcap, lane, thr, pos);
+                        }
+                    }
+                }
+            }
+            if (lane == 0) tseg[warp] = thr;
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3: count, reserve, write — survivors of this block's 32 streams in stream order
+    float T = INFINITY;
+    if (s < fp.S) T = fminf(tlocal[s], tseg[s / G]);
     int mine = 0;
-    for (int base = 0; base < n_log; base += 32) {
+#pragma unroll
+    for (int i = 0; i < kLogRegs; ++i) mine += __popc(__ballot_sync(0xFFFFFFFFu, __uint_as_float(ereg[i].x) < T));
+    for (int base = kLogRegs * 32; base < n_log; base += 32) {
         const int j = base + lane;
         const bool keep = (j < n_log) && (__uint_as_float(lg[j].x) < T);
         mine += __popc(__ballot_sync(0xFFFFFFFFu, keep));
@@ -544,7 +611,15 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
     }
     __syncthreads();
     int wr = blk_base + woff[warp];
-    for (int base = 0; base < n_log; base += 32) {
+#pragma unroll
+    for (int i = 0; i < kLogRegs; ++i) {
+        const bool keep = __uint_as_float(ereg[i].x) < T;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+        const int off = wr + __popc(m & ((1u << lane) - 1u));
+        if (keep && off < fp.outcap) fp.out[off] = ereg[i];
+        wr += __popc(m);
+    }
+    for (int base = kLogRegs * 32; base < n_log; base += 32) {
         const int j = base + lane;
         uint2 e = make_uint2(0, 0);
         bool keep = false;
@@ -554,8 +629,9 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
         if (keep && off < fp.outcap) fp.out[off] = e;
         wr += __popc(m);
     }
-    // last block publishes the header and re-arms the control words for the next query
-    __threadfence_system();
+    // last block publishes the header and re-arms the control words for the next query.  The host only reads the
+    // mapped buffers after the stream has drained, so device-scope ordering between blocks is all that is needed.
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const int done = atomicAdd(&fp.ctrl[2], 1);
@@ -564,7 +640,6 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
             const int ovf = atomicAdd(&fp.ctrl[1], 0);
             fp.hdr[0] = total;
             fp.hdr[1] = (ovf != 0 || total > fp.outcap) ? 1 : 0;
-            __threadfence_system();
             fp.hdr[2] = fp.seqno;
             fp.ctrl[0] = 0; fp.ctrl[1] = 0; fp.ctrl[2] = 0;
         }

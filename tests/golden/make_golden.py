@@ -90,5 +90,21 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--sql" not in sys.argv:
     main()
+
+
+def sql_golden():
+    """SQL-level outputs of the unmodified reference extension (stock build, backend 'CPU')."""
+    import json
+    from tests import sql_cases
+    from tests.sqlrun import REF_CPU, run_sql
+    for name, script in (("sql_surface.json", sql_cases.surface_script()), ("sql_scan.json", sql_cases.scan_script())):
+        res = run_sql(REF_CPU, script)
+        with open(os.path.join(OUT, name), "w") as f:
+            json.dump(res, f)
+        print(name, os.path.getsize(os.path.join(OUT, name)), "bytes,", sum("error" in r for r in res), "error results")
+
+
+if __name__ == "__main__" and "--sql" in sys.argv:
+    sql_golden()
