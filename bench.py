@@ -296,7 +296,7 @@ def main():
         e2e_s = float(t.item())
 
     avg_surv = (ix.stat("survivors") - surv0) / max(ix.stat("queries") - q0, 1)
-    d2h_bytes = int(round(avg_surv * 8 + ix.stat("filter_blocks") * 8 + 12))
+    d2h_bytes = int(ix.stat("fetch_bytes"))  # header + block table + first 1024 candidate slots, one cudaMemcpyAsync per query
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -325,7 +325,7 @@ def main():
                    "result_mode": "exact reference slot replay (bit-exact rowids/order/distances vs distance-cpu.c)"},
         "e2e": {"value": K / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(pitch),
                 "d2h_bytes_per_step": d2h_bytes, "avg_candidates_per_query": avg_surv,
-                "note": "vsb_scan_topk: pinned query H2D + scan/filter kernels + zero-copy readback of the surviving candidates (8 B each) + host slot replay"},
+                "note": "vsb_scan_topk: pinned query H2D + scan/filter kernels + one D2H copy of the candidate block (header + table + 1024 slots) + host slot replay"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "vsb::scan_kernel<int8,L2>", "avg_launch_ms": scan_ms, "launches_timed": prof["scan_launches"],

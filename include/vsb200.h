@@ -108,7 +108,7 @@ VSB_API int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query
 /* blocks until the engine stream is idle and converts the last device-side result into top-k. */
 VSB_API int vsb_collect_last(vsb_index *ix, int k, int64_t *out_rowids, double *out_dist, int *out_count);
 VSB_API int vsb_index_query_pitch(const vsb_index *ix); /* bytes per query row on the device (multiple of 16) */
-/* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks"}; -1 if unknown */
+/* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes"}; -1 if unknown */
 VSB_API int64_t vsb_index_stat(const vsb_index *ix, const char *name);
 VSB_API void *vsb_index_stream(vsb_index *ix);           /* cudaStream_t of the engine, for event timing */
 /* kernel launch counter (all kernels launched by this library since load) */

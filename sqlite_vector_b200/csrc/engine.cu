@@ -66,8 +66,17 @@ constexpr int kOutCap = 1 << 16;         // survivor capacity per query (mapped 
 constexpr int kMaxK = 256;               // candidate path; larger k uses the all-distances path
 constexpr int kSlots = 2;                // result slots (pipelining of batches)
 
+// result block of one query, written by filter_kernel into DEVICE memory and fetched with one async copy:
+//   [hdr: 16 ints][table: kTableCap x int2][survivors: kOutCap x uint2]; the first kFirstFetch survivors travel
+//   with the header, the (rare) rest in a second copy.  (Zero-copy writes of ~300 scattered 8-byte records over
+//   PCIe made the filter kernel 5x slower than writing to HBM and copying once.)
+constexpr int kTableCap = 512;
+constexpr int kFirstFetch = 1024;
+constexpr size_t kResHdrBytes = 64 + sizeof(int2) * kTableCap;
+
 struct Slot {
-    uint2 *h_out = nullptr, *d_out = nullptr;  // mapped pinned survivors
+    uint8_t *d_res = nullptr, *h_res = nullptr;
+    uint2 *h_out = nullptr, *d_out = nullptr;
     int2 *h_table = nullptr, *d_table = nullptr;
     int *h_hdr = nullptr, *d_hdr = nullptr;
     uint8_t *h_query = nullptr, *d_query = nullptr;  // pinned staging + device copy of the query
@@ -179,13 +188,14 @@ int ensure_slots(vsb_index *ix) {
     if (ix->slots_ready) return VSB_OK;
     for (int i = 0; i < kSlots; ++i) {
         Slot &s = ix->slot[i];
-        CU(cudaHostAlloc((void **)&s.h_out, sizeof(uint2) * kOutCap, cudaHostAllocMapped));
-        CU(cudaHostGetDevicePointer((void **)&s.d_out, s.h_out, 0));
-        CU(cudaHostAlloc((void **)&s.h_table, sizeof(int2) * 4096, cudaHostAllocMapped));
-        CU(cudaHostGetDevicePointer((void **)&s.d_table, s.h_table, 0));
-        CU(cudaHostAlloc((void **)&s.h_hdr, sizeof(int) * 16, cudaHostAllocMapped));
-        CU(cudaHostGetDevicePointer((void **)&s.d_hdr, s.h_hdr, 0));
-        memset(s.h_hdr, 0, sizeof(int) * 16);
+        const size_t res_bytes = kResHdrBytes + sizeof(uint2) * kOutCap;
+        CU(cudaMalloc((void **)&s.d_res, res_bytes));
+        CU(cudaMemset(s.d_res, 0, kResHdrBytes));
+        CU(cudaHostAlloc((void **)&s.h_res, res_bytes, cudaHostAllocDefault));
+        memset(s.h_res, 0, kResHdrBytes);
+        s.d_hdr = (int *)s.d_res; s.h_hdr = (int *)s.h_res;
+        s.d_table = (int2 *)(s.d_res + 64); s.h_table = (int2 *)(s.h_res + 64);
+        s.d_out = (uint2 *)(s.d_res + kResHdrBytes); s.h_out = (uint2 *)(s.h_res + kResHdrBytes);
         CU(cudaHostAlloc((void **)&s.h_query, (size_t)ix->pitch, cudaHostAllocDefault));
         CU(cudaMalloc((void **)&s.d_query, (size_t)ix->pitch));
         CU(cudaMalloc((void **)&s.d_ctrl, sizeof(int) * 4));
@@ -277,7 +287,7 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         const int nblocks = (f.S + kFilterWarps - 1) / kFilterWarps;
         slot->nblocks = nblocks;
         const size_t fsm_base = sizeof(float) * ((size_t)2 * kFilterWarps * kcap + (size_t)f.S + 32);
-        const size_t fsm_fast = fsm_base + sizeof(float) * (size_t)f.S * k;
+        const size_t fsm_fast = fsm_base + sizeof(float) * (size_t)f.S * 32;
         const bool fast = (k <= 32) && fsm_fast + 2048 <= (size_t)ix->max_smem;
         if (fast) {
             CU(cudaFuncSetAttribute((const void *)filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm_fast));
@@ -289,6 +299,8 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         CU(cudaGetLastError());
         ++g_launches;
         if (pev) CU(cudaEventRecord(pev[2], ix->stream));
+        if (nblocks > kTableCap) return fail(VSB_ERANGE, "too many filter blocks (%d)", nblocks);
+        CU(cudaMemcpyAsync(slot->h_res, slot->d_res, kResHdrBytes + sizeof(uint2) * kFirstFetch, cudaMemcpyDeviceToHost, ix->stream));
     }
     return VSB_OK;
 }
@@ -338,6 +350,12 @@ int gather_survivors(vsb_index *ix, Slot *slot, std::vector<uint2> &out, bool *o
     if (slot->h_hdr[2] != slot->seq) return fail(VSB_ECUDA, "scan result header not published (seq %d != %d)", slot->h_hdr[2], slot->seq);
     if (slot->h_hdr[1]) { *overflow = true; return 0; }
     const int total = slot->h_hdr[0];
+    if (total > kFirstFetch) {  // rare: fetch the tail of the survivor list
+        if (cudaMemcpyAsync(slot->h_out + kFirstFetch, slot->d_out + kFirstFetch, sizeof(uint2) * (size_t)(total - kFirstFetch),
+                            cudaMemcpyDeviceToHost, ix->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ix->stream) != cudaSuccess)
+            return fail(VSB_ECUDA, "fetching %d survivors failed: %s", total, cudaGetErrorString(cudaGetLastError()));
+    }
     out.clear();
     out.reserve((size_t)total);
     for (int b = 0; b < slot->nblocks; ++b) {
@@ -603,6 +621,7 @@ int64_t vsb_index_stat(const vsb_index *ix, const char *name) {
     if (!strcmp(name, "survivors")) return ix->st_survivors;
     if (!strcmp(name, "last_survivors")) return ix->st_last_survivors;
     if (!strcmp(name, "fallbacks")) return ix->st_fallbacks;
+    if (!strcmp(name, "fetch_bytes")) return (long long)(kResHdrBytes + sizeof(uint2) * kFirstFetch);
     if (!strcmp(name, "filter_blocks")) return (ix->num_sms * kWarps + kFilterWarps - 1) / kFilterWarps;
     return -1;
 }
@@ -618,9 +637,8 @@ void vsb_index_free(vsb_index *ix) {
     }
     for (int i = 0; i < kSlots; ++i) {
         Slot &s = ix->slot[i];
-        if (s.h_out) cudaFreeHost(s.h_out);
-        if (s.h_table) cudaFreeHost(s.h_table);
-        if (s.h_hdr) cudaFreeHost(s.h_hdr);
+        if (s.h_res) cudaFreeHost(s.h_res);
+        if (s.d_res) cudaFree(s.d_res);
         if (s.h_query) cudaFreeHost(s.h_query);
         if (s.d_query) cudaFree(s.d_query);
         if (s.d_ctrl) cudaFree(s.d_ctrl);

@@ -446,6 +446,7 @@ struct FilterParams {
 };
 
 constexpr int kFilterWarps = 32;
+constexpr int kSegments = 8;  // threshold segments: few long serial walks beat many short ones (issue-bound otherwise)
 constexpr int kLogRegs = 8;   // log entries per lane prefetched into registers (256 per stream)
 
 __device__ __forceinline__ float funkey(uint32_t k) {  // inverse of fkey
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
     __shared__ int blk_base;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = (fp.S + kFilterWarps - 1) / kFilterWarps;                 // streams per segment
+    const int G = (fp.S + kSegments - 1) / kSegments;                       // streams per segment
 
     // ---- issue this warp's log loads first: they do not depend on the thresholds
     const int s = blockIdx.x * kFilterWarps + warp;
@@ -506,24 +507,21 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
 
     if constexpr (FAST) {
         // all stream lists -> shared memory, fully parallel and coalesced
-        const int total = fp.S * k;
-        for (int i = threadIdx.x; i < total; i += kFilterWarps * 32) {
-            const int st = i / k, j = i - st * k;
-            slists[i] = fp.lists[(size_t)st * kcap + j];
-        }
+        for (int st = warp; st < fp.S; st += kFilterWarps)                  // one (padded) list per warp iteration, no division
+            slists[st * 32 + lane] = fp.lists[(size_t)st * kcap + lane];    // kcap == 32 on this path; entries >= k are -INF
         __syncthreads();
-        {   // phase 1: warp g walks segment g in stream order, recording the running k-th value before each stream
+        if (warp < kSegments) {   // phase 1: warp g walks segment g in stream order, recording the running k-th value before each stream
             RegList L;
             L.init(lane, k);
             const int s0 = warp * G, s1 = min(fp.S, s0 + G);
             for (int st = s0; st < s1; ++st) {
                 if (lane == 0) tlocal[st] = L.thr;
-                L.offer(lane, (lane < k) ? slists[st * k + lane] : INFINITY);
+                L.offer(lane, (lane < k) ? slists[st * 32 + lane] : INFINITY);
             }
             seglist[warp * kcap + lane] = L.v;
         }
         __syncthreads();
-        {   // phase 2: warp g merges the lists of segments 0..g-1
+        if (warp < kSegments) {   // phase 2: warp g merges the lists of segments 0..g-1
             RegList L;
             L.init(lane, k);
             for (int g = 0; g < warp; ++g) L.offer(lane, (lane < k) ? seglist[g * kcap + lane] : INFINITY);
@@ -532,7 +530,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
         __syncthreads();
     } else {
         // generic path (any k): lists stay in global memory / L2, k-lists in shared memory
-        {
+        if (warp < kSegments) {
             float *L = seglist + warp * kcap;
             for (int j = lane; j < kcap; j += 32) L[j] = (j < k) ? INFINITY : -INFINITY;
             __syncwarp();
@@ -560,7 +558,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
             }
         }
         __syncthreads();
-        {
+        if (warp < kSegments) {
             float *L = work + warp * kcap;
             for (int j = lane; j < kcap; j += 32) L[j] = (j < k) ? INFINITY : -INFINITY;
             __syncwarp();
