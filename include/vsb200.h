@@ -82,7 +82,10 @@ VSB_API void vsb_index_free(vsb_index *ix);
  * For query b the results are out_rowids[b*k .. b*k+out_counts[b]) / out_dist[...] in the
  * reference's output order (distance ascending, reference tie order), distances widened to
  * double exactly like the cursor's distance[] array (:1804, :2011).
- * max_index (in/out, may be NULL): the cursor's slot index quirk (:1808-1813 never resets it). */
+ * max_index (in/out, may be NULL, nq == 1 only): the cursor's slot index quirk (:1808-1813 never resets it).
+ * nq > 1 has no counterpart in the reference (one vector per xFilter); each query then behaves like a fresh cursor.
+ * For nq >= 16 on f16/bf16/int8/uint8 columns with L2/SQUARED_L2/COSINE/DOT the scores are computed on the tensor
+ * cores (tcgen05) and refined exactly; results are the same as nq single calls. */
 VSB_API int vsb_scan_topk(vsb_index *ix, int metric, const void *queries, int nq, int k, int64_t *out_rowids,
                           double *out_dist, int *out_counts, int *max_index);
 
@@ -108,7 +111,7 @@ VSB_API int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query
 /* blocks until the engine stream is idle and converts the last device-side result into top-k. */
 VSB_API int vsb_collect_last(vsb_index *ix, int k, int64_t *out_rowids, double *out_dist, int *out_count);
 VSB_API int vsb_index_query_pitch(const vsb_index *ix); /* bytes per query row on the device (multiple of 16) */
-/* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes"}; -1 if unknown */
+/* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes","batches","batch_cands","batch_kept"}; -1 if unknown */
 VSB_API int64_t vsb_index_stat(const vsb_index *ix, const char *name);
 VSB_API void *vsb_index_stream(vsb_index *ix);           /* cudaStream_t of the engine, for event timing */
 /* kernel launch counter (all kernels launched by this library since load) */
@@ -116,7 +119,7 @@ VSB_API int64_t vsb_kernel_launches(void);
 /* with option "time_kernels"=1 every launch is bracketed by CUDA events on the engine stream; this returns
  * (and resets) the summed device time and launch count of the scan kernel and of the filter kernel. */
 VSB_API int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double *filter_ms, int *filter_launches);
-/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels"}; returns previous value */
+/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch"}; returns previous value */
 VSB_API int vsb_set_option(const char *name, int value);
 
 #ifdef __cplusplus

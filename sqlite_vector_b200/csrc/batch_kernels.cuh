@@ -1,0 +1,488 @@
+// batch_kernels.cuh — batched-query path: tcgen05 tensor-core scoring + exact candidate refinement.
+//
+// For B queries against the resident shard the scores  S[row][q] = <row, query_q>  are a dense GEMM
+// (rows x dim) x (dim x B): this is the one place where the scan IS tensor-core work (north_star).
+// tc_scan_kernel computes S tile by tile with tcgen05.mma (A = 128 corpus rows, B = up to 256 queries, both K-major
+// in 128B-swizzled shared memory filled by TMA, accumulators in TMEM) and NEVER materialises S: the epilogue reads
+// the accumulators back with tcgen05.ld and only tests each score against a per-query bound, appending the rare
+// hits (row, query) to a candidate log.  The bound is conservative (it absorbs the tensor-core rounding), so the log
+// is a superset of the rows whose EXACT reference distance beats the query's running k-th distance; the refinement
+// kernels below recompute those distances with exactly the arithmetic of the single-query kernel (accum16/finalize)
+// and replay the reference's slot algorithm (src/sqlite-vector.c:2022-2069, 2145-2152) per query, level by level.
+#pragma once
+#include <cuda.h>
+
+#include "scan_kernels.cuh"
+
+namespace vsb {
+
+enum { TK_BF16 = 0, TK_F16 = 1, TK_I8 = 2, TK_U8 = 3 };
+constexpr int kTcThreads = 256;     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue
+constexpr int kTcStages = 4;
+constexpr int kTcM = 128;           // corpus rows per MMA tile
+constexpr int kTcKBytes = 128;      // one swizzle atom of K per stage
+
+struct TcParams {
+    long long r0, r1;       // row range of this level (r0 multiple of 128)
+    long long n;            // rows in the shard
+    int nq;                 // queries
+    int N;                  // MMA N: 32, 64, 128 or 256 queries per tile
+    int NG;                 // query groups = ceil(nq / N)
+    int KB;                 // 128-byte K blocks per row
+    int mc;                 // MC_L2 / MC_COS / MC_DOT
+    const float *qc;        // [NG*N] per-query constant (float, or int bit pattern for the integer kinds)
+    const void *norms;      // [n] float (fp kinds) or int (integer kinds): sum of squares of each row
+    uint2 *cand;            // (row, query)
+    unsigned *cand_count;
+    unsigned cand_cap;
+};
+
+// ------------------------------------------------------------------ PTX wrappers (tcgen05 / TMA)
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+template <bool INT8>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (INT8) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    }
+}
+// 32 lanes x 32 columns of 32-bit accumulators -> 32 registers per thread (lane = TMEM lane, i.e. corpus row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in 128B-swizzled shared memory (rows of 128 bytes, 8-row groups 1024 B apart):
+// start address >> 4 | LBO = 1 | SBO = 1024 >> 4 | version 1 (Blackwell) | layout SWIZZLE_128B (2)   [cute/arch/mma_sm100_desc.hpp]
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
+    const uint64_t addr = (uint64_t)((smem_u32(smem) & 0x3FFFFu) >> 4);
+    return addr | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// instruction descriptor: D format bits [4,6), A/B formats [7,10)/[10,13), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ inline uint32_t umma_idesc(int kind, int N) {
+    uint32_t cfmt, abfmt;
+    switch (kind) {
+    case TK_BF16: cfmt = 1; abfmt = 1; break;   // F32 accumulate, BF16 inputs
+    case TK_F16: cfmt = 1; abfmt = 0; break;    // F32 accumulate, F16 inputs
+    case TK_I8: cfmt = 2; abfmt = 1; break;     // S32 accumulate, signed 8-bit
+    default: cfmt = 2; abfmt = 0; break;        // S32 accumulate, unsigned 8-bit
+    }
+    return (cfmt << 4) | (abfmt << 7) | (abfmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+}
+
+// the per-element candidate test.  fp kinds use negated comparisons so that NaN scores count as hits.
+template <bool INT8>
+__device__ __forceinline__ bool tc_hit(int mc, uint32_t sbits, uint32_t qcbits, float rowf, int rowi) {
+    if constexpr (INT8) {
+        const int s = (int)sbits;
+        if (mc == MC_DOT) return s > (int)qcbits;
+        if (mc == MC_L2) return (2 * s + rowi) >= (int)qcbits;                 // rowi = -|row|^2
+        return !(fmaf(-__uint_as_float(qcbits), rowf, (float)s) < 0.0f);       // cosine: rowf = |row|
+    } else {
+        const float s = __uint_as_float(sbits), qc = __uint_as_float(qcbits);
+        if (mc == MC_DOT) return !(s <= qc);
+        if (mc == MC_L2) return !(fmaf(2.0f, s, rowf) <= qc);                  // rowf = -|row|^2 (1 - e)
+        return !(fmaf(-qc, rowf, s) < 0.0f);                                   // cosine: rowf = |row|
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB, const TcParams prm) {
+    constexpr bool INT8 = (KIND == TK_I8 || KIND == TK_U8);
+    extern __shared__ __align__(1024) uint8_t tsm[];
+    const int N = prm.N;
+    const uint32_t a_bytes = kTcM * kTcKBytes, b_bytes = (uint32_t)N * kTcKBytes, stage_bytes = a_bytes + b_bytes;
+    uint8_t *stages = tsm;                                                     // [kTcStages][A | B], 1024-aligned
+    uint64_t *full = reinterpret_cast<uint64_t *>(tsm + kTcStages * stage_bytes);
+    uint64_t *empty = full + kTcStages;
+    uint64_t *tfull = empty + kTcStages;                                       // [2] accumulator ready
+    uint64_t *tempty = tfull + 2;                                              // [2] accumulator drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint32_t *qc_s = tmem_slot + 4;                                            // [NG*N]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_cols = (2 * N <= 32) ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kTcStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+    for (int i = threadIdx.x; i < prm.NG * N; i += kTcThreads) qc_s[i] = __float_as_uint(prm.qc[i]);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long mt0 = prm.r0 / kTcM, mt1 = (prm.r1 + kTcM - 1) / kTcM;    // corpus tiles of this level
+    const long long ntile = (mt1 - mt0) * prm.NG;                              // (corpus tile, query group) pairs, group fastest
+
+    if (warp == 0) {
+        if (lane == 0) {                                                       // ===== TMA producer
+            int it = 0;
+            for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
+                const long long mt = mt0 + t / prm.NG;
+                const int ng = (int)(t % prm.NG);
+                for (int kb = 0; kb < prm.KB; ++kb, ++it) {
+                    const int s = it % kTcStages;
+                    mbar_wait(&empty[s], (uint32_t)(((it / kTcStages) & 1) ^ 1));
+                    mbar_expect_tx(&full[s], stage_bytes);
+                    uint8_t *st = stages + (size_t)s * stage_bytes;
+                    tma_load_2d(st, &tmA, kb * kTcKBytes, (int)(mt * kTcM), &full[s]);
+                    tma_load_2d(st + a_bytes, &tmB, kb * kTcKBytes, ng * N, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                                       // ===== MMA issuer (one thread)
+            const uint32_t idesc = umma_idesc(KIND, N);
+            int it = 0, tl = 0;
+            for (long long t = blockIdx.x; t < ntile; t += gridDim.x, ++tl) {
+                const int as = tl & 1;
+                mbar_wait(&tempty[as], (uint32_t)(((tl >> 1) & 1) ^ 1));
+                tc_fence_after();
+                for (int kb = 0; kb < prm.KB; ++kb, ++it) {
+                    const int s = it % kTcStages;
+                    mbar_wait(&full[s], (uint32_t)((it / kTcStages) & 1));
+                    tc_fence_after();
+                    const uint8_t *st = stages + (size_t)s * stage_bytes;
+                    const uint64_t ad = umma_desc_sw128(st), bd = umma_desc_sw128(st + a_bytes);
+#pragma unroll
+                    for (int k4 = 0; k4 < kTcKBytes / 32; ++k4)                // UMMA_K = 32 bytes: advance start address by 2 (x16 B)
+                        tc_mma<INT8>(tmem_base + (uint32_t)(as * N), ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idesc, (uint32_t)((kb | k4) != 0));
+                    tc_commit(&empty[s]);                                      // frees the smem stage when these MMAs retire
+                }
+                tc_commit(&tfull[as]);                                         // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {                                                    // ===== epilogue: TMEM -> registers -> threshold test
+        const int quad = warp & 3;
+        int tl = 0;
+        for (long long t = blockIdx.x; t < ntile; t += gridDim.x, ++tl) {
+            const long long mt = mt0 + t / prm.NG;
+            const int ng = (int)(t % prm.NG);
+            const int as = tl & 1;
+            const long long row = mt * kTcM + quad * 32 + lane;
+            const bool rowvalid = row >= prm.r0 && row < prm.r1;
+            float rowf = 0.0f;
+            int rowi = 0;
+            if (rowvalid) {
+                if constexpr (INT8) {
+                    const int nn = reinterpret_cast<const int *>(prm.norms)[row];
+                    rowi = -nn;
+                    rowf = (KIND == TK_U8) ? __fsqrt_rn((float)(uint32_t)nn) : __fsqrt_rn((float)nn);
+                } else {
+                    const float nn = reinterpret_cast<const float *>(prm.norms)[row];
+                    rowf = (prm.mc == MC_L2) ? -nn * (1.0f - 1e-4f) : __fsqrt_rn(nn);
+                }
+            }
+            mbar_wait(&tfull[as], (uint32_t)((tl >> 1) & 1));
+            tc_fence_after();
+            for (int cb = 0; cb < N; cb += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * N + cb), v);
+                const uint32_t *qc = qc_s + ng * N + cb;
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) any |= tc_hit<INT8>(prm.mc, v[j], qc[j], rowf, rowi);
+                any = any && rowvalid;
+                if (__ballot_sync(0xFFFFFFFFu, any)) {                         // rare: append (row, query) hits, one atomic per warp
+                    uint32_t mask = 0;
+                    if (any) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mask |= (tc_hit<INT8>(prm.mc, v[j], qc[j], rowf, rowi) ? 1u : 0u) << j;
+                        const int ncol = prm.nq - (ng * N + cb);                // padded query columns are never reported
+                        mask &= (ncol >= 32) ? 0xFFFFFFFFu : (ncol <= 0 ? 0u : ((1u << ncol) - 1u));
+                    }
+                    const int mine = __popc(mask);
+                    int incl = mine;
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                        if (lane >= off) incl += o;
+                    }
+                    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    unsigned base = 0;
+                    if (lane == 31) base = atomicAdd(prm.cand_count, (unsigned)total);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+                    unsigned w = base + (unsigned)(incl - mine);
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int q = ng * N + cb + j;
+                        if (w < prm.cand_cap) prm.cand[w] = make_uint2((uint32_t)row, (uint32_t)q);
+                        ++w;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------ row norms (once per resident shard)
+template <int VT>
+__global__ void row_norm_kernel(const uint8_t *vec, long long n, int pitch, void *out) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const uint4 *p = reinterpret_cast<const uint4 *>(vec + (size_t)row * pitch);
+    float f = 0.0f;
+    int iq = 0;
+    for (int c = lane; c < pitch / 16; c += 32) {
+        const uint4 q = ldg_stream(p + c);
+        if constexpr (VT == T_U8) {
+            iq = (int)__dp4a(q.x, q.x, (uint32_t)iq); iq = (int)__dp4a(q.y, q.y, (uint32_t)iq);
+            iq = (int)__dp4a(q.z, q.z, (uint32_t)iq); iq = (int)__dp4a(q.w, q.w, (uint32_t)iq);
+        } else if constexpr (VT == T_I8) {
+            iq = __dp4a((int)q.x, (int)q.x, iq); iq = __dp4a((int)q.y, (int)q.y, iq);
+            iq = __dp4a((int)q.z, (int)q.z, iq); iq = __dp4a((int)q.w, (int)q.w, iq);
+        } else {
+            float x[8];
+            unpack8<VT>(q, x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f = fmaf(x[j], x[j], f);
+        }
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        f += __shfl_xor_sync(0xFFFFFFFFu, f, off);
+        iq += __shfl_xor_sync(0xFFFFFFFFu, iq, off);
+    }
+    if (lane == 0) {
+        if constexpr (VT == T_U8 || VT == T_I8) reinterpret_cast<int *>(out)[row] = iq;
+        else reinterpret_cast<float *>(out)[row] = f;
+    }
+}
+
+// ------------------------------------------------------------------ exact refinement
+// level 0: every (row, query) pair of the first m0 rows is a candidate
+__global__ void all_pairs_kernel(uint2 *cand, unsigned *count, long long m0, int nq) {
+    const long long total = m0 * nq;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        cand[i] = make_uint2((uint32_t)(i % m0), (uint32_t)(i / m0));
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count = (unsigned)total;
+}
+
+struct RefineParams {
+    const uint8_t *vec;      // [n][pitch]
+    const uint8_t *queries;  // [nq][pitch] zero padded
+    int pitch, root;
+    const uint2 *cand;
+    const unsigned *cand_count;
+    unsigned cand_cap;
+    const float *U;          // [nq] exact distance bound of this level (strict <)
+    unsigned long long *kept_key;   // (query << 32) | row
+    float *kept_val;
+    unsigned *kept_count;
+    unsigned kept_cap;
+};
+
+// one warp per candidate: the reference distance with the arithmetic of the single-query kernel
+template <int VT, int MC>
+__global__ void refine_kernel(const RefineParams rp) {
+    const unsigned ncand = min(*rp.cand_count, rp.cand_cap);
+    const int lane = threadIdx.x & 31;
+    const unsigned wpb = blockDim.x >> 5;
+    const int nc = rp.pitch / 16;
+    for (unsigned c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncand; c += gridDim.x * wpb) {
+        const uint2 cq = rp.cand[c];
+        const uint4 *rowp = reinterpret_cast<const uint4 *>(rp.vec + (size_t)cq.x * rp.pitch);
+        const uint4 *qp = reinterpret_cast<const uint4 *>(rp.queries + (size_t)cq.y * rp.pitch);
+        Accum A = {0.f, 0.f, 0.f, 0.f, 0, 0, 0};
+        QueryNorm qn = {0.f, 0};
+        for (int i = lane; i < nc; i += 32) {
+            const uint4 rv = __ldg(rowp + i), qv = __ldg(qp + i);
+            accum16<VT, MC>(A, rv, qv);
+            if constexpr (VT == T_U8) {
+                qn.i = (int)__dp4a(qv.x, qv.x, (uint32_t)qn.i); qn.i = (int)__dp4a(qv.y, qv.y, (uint32_t)qn.i);
+                qn.i = (int)__dp4a(qv.z, qv.z, (uint32_t)qn.i); qn.i = (int)__dp4a(qv.w, qv.w, (uint32_t)qn.i);
+            } else if constexpr (VT == T_I8) {
+                qn.i = __dp4a((int)qv.x, (int)qv.x, qn.i); qn.i = __dp4a((int)qv.y, (int)qv.y, qn.i);
+                qn.i = __dp4a((int)qv.z, (int)qv.z, qn.i); qn.i = __dp4a((int)qv.w, (int)qv.w, qn.i);
+            } else if constexpr (MC == MC_COS) {
+                float x[8];
+                unpack8<VT>(qv, x);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) qn.f = fmaf(x[j], x[j], qn.f);
+            }
+        }
+        accum_reduce(A, 32);
+        for (int off = 16; off >= 1; off >>= 1) {
+            qn.f += __shfl_xor_sync(0xFFFFFFFFu, qn.f, off);
+            qn.i += __shfl_xor_sync(0xFFFFFFFFu, qn.i, off);
+        }
+        const float d = finalize<VT, MC>(A, qn, rp.root);
+        if (lane == 0 && d < rp.U[cq.y]) {
+            const unsigned w = atomicAdd(rp.kept_count, 1u);
+            if (w < rp.kept_cap) {
+                rp.kept_key[w] = ((unsigned long long)cq.y << 32) | cq.x;
+                rp.kept_val[w] = d;
+            }
+        }
+    }
+}
+
+// per-query slot state carried across levels (the reference's cursor arrays, src/sqlite-vector.c:1808-1813)
+struct ReplayParams {
+    const unsigned long long *key;   // sorted (query, row)
+    const float *val;
+    const unsigned *count;
+    unsigned cap;
+    int nq, k, kcap;
+    float *slot_d;          // [nq][kcap]
+    unsigned *slot_row;     // [nq][kcap]
+    int *slot_mi;           // [nq] max_index
+    float *U;               // [nq] out: running k-th distance after this level
+    float *qc;              // [NGN] out: conservative constant for the next level
+    int mc, kind, root;
+    const void *qnorm;      // [nq] float / int sum of squares of each query
+    float rnmax;            // max row norm (fp kinds, DOT slack)
+    int level0;             // 1: initialise the slots first
+};
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// conservative per-query constant for tc_hit from the exact bound U
+__device__ inline float conservative_qc(int kind, int mc, int root, float U, const void *qnorm, int q, float rnmax) {
+    const bool INT8 = (kind == TK_I8 || kind == TK_U8);
+    if (INT8) {
+        const int qi = reinterpret_cast<const int *>(qnorm)[q];
+        const double qq = (kind == TK_U8) ? (double)(uint32_t)qi : (double)qi;
+        if (mc == MC_DOT) {          // d = -(float)s < U  <=  s > -U - 1 - 2e-7|U|
+            double b = -(double)U - 1.0 - 2e-7 * fabs((double)U);
+            if (!(U < 3.0e38f)) b = -2147483647.0;
+            b = fmin(fmax(floor(b), -2147483647.0), 2147483646.0);
+            return __int_as_float((int)b);
+        }
+        if (mc == MC_L2) {           // d2 = qq + nn - 2s <= d2max  <=>  2s - nn >= qq - d2max
+            double u2 = root ? (double)U * (double)U : (double)U;
+            double d2max = ceil(u2 * (1.0 + 1e-6)) + 1.0;
+            if (!(U < 3.0e38f) || !(d2max < 4.0e9)) d2max = 4.0e9;
+            double b = fmin(fmax(qq - d2max, -2147483647.0), 2147483646.0);
+            return __int_as_float((int)b);
+        }
+        const float u = fminf(U, 3.0e38f);                                       // cosine
+        return clampf((1.0f - u - 1e-5f) * sqrtf((float)qq), -1e30f, 1e30f);
+    }
+    const float qq = reinterpret_cast<const float *>(qnorm)[q];
+    if (!(U < 3.0e38f)) return (mc == MC_COS) ? -1e30f : -INFINITY;
+    if (mc == MC_DOT) return -U - 1e-4f * sqrtf(qq) * rnmax - 1e-30f;
+    if (mc == MC_L2) {
+        const float u2 = root ? U * U : U;
+        return qq * (1.0f - 1e-4f) - u2 * (1.0f + 1e-5f) - 1e-30f;
+    }
+    return clampf((1.0f - U - 1e-4f) * sqrtf(qq), -1e30f, 1e30f);
+}
+
+// one warp per query: feed this level's kept candidates (sorted by row) through the reference's slot update
+__global__ void replay_kernel(const ReplayParams rp) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= rp.nq) return;
+    float *sd = rp.slot_d + (size_t)q * rp.kcap;
+    unsigned *sr = rp.slot_row + (size_t)q * rp.kcap;
+    if (rp.level0) {
+        for (int j = lane; j < rp.kcap; j += 32) { sd[j] = (j < rp.k) ? INFINITY : -INFINITY; sr[j] = 0; }
+        if (lane == 0) rp.slot_mi[q] = 0;
+        __syncwarp();
+    }
+    // this query's segment of the sorted key array
+    const unsigned n = min(*rp.count, rp.cap);
+    const unsigned long long lo_key = (unsigned long long)q << 32, hi_key = (unsigned long long)(q + 1) << 32;
+    unsigned a = 0, b = n;
+    while (a < b) { const unsigned m = (a + b) >> 1; if (rp.key[m] < lo_key) a = m + 1; else b = m; }
+    const unsigned seg0 = a;
+    b = n;
+    while (a < b) { const unsigned m = (a + b) >> 1; if (rp.key[m] < hi_key) a = m + 1; else b = m; }
+    const unsigned seg1 = a;
+    int mi = rp.slot_mi[q];
+    float cur = sd[mi];
+    for (unsigned base = seg0; base < seg1; base += 32) {
+        const unsigned i = base + lane;
+        const float d = (i < seg1) ? rp.val[i] : INFINITY;
+        const unsigned row = (i < seg1) ? (unsigned)(rp.key[i] & 0xFFFFFFFFu) : 0u;
+        unsigned m = __ballot_sync(0xFFFFFFFFu, d < cur);
+        while (m) {
+            const int sl = __ffs(m) - 1;
+            m &= m - 1;
+            const float dv = __shfl_sync(0xFFFFFFFFu, d, sl);
+            const unsigned rv = __shfl_sync(0xFFFFFFFFu, row, sl);
+            if (dv < cur) {                                   // strict, src/sqlite-vector.c:2145
+                if (lane == 0) { sd[mi] = dv; sr[mi] = rv; }
+                __syncwarp();
+                // first index holding the maximum (vFullScanFindMaxIndex, :2022-2049)
+                float best = -INFINITY;
+                int bi = 0x7FFFFFFF;
+                for (int j = lane; j < rp.kcap; j += 32) {
+                    const float v = sd[j];
+                    if (v > best) { best = v; bi = j; }
+                }
+                const uint32_t key = fkey(best);
+                const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, key);
+                const int cand = (key == mx) ? bi : 0x7FFFFFFF;
+                mi = __reduce_min_sync(0xFFFFFFFFu, cand);
+                cur = funkey(mx);
+            }
+        }
+    }
+    if (lane == 0) {
+        rp.slot_mi[q] = mi;
+        rp.U[q] = cur;
+        rp.qc[q] = conservative_qc(rp.kind, rp.mc, rp.root, cur, rp.qnorm, q, rp.rnmax);
+    }
+}
+
+__global__ void fill_kernel(float *p, float v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void max_norm_kernel(const float *norms, long long n, float *out) {   // out must be zeroed; norms >= 0
+    float m = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, norms[i]);
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));
+}
+
+}  // namespace vsb

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "scan_kernels.cuh"
+#include "batch_kernels.cuh"
 
 using namespace vsb;
 
@@ -32,6 +33,7 @@ std::atomic<long long> g_launches{0};
 int g_opt_stage_bytes = 8192;  // target bytes of one warp tile (ring stage)
 int g_opt_direct = 0;          // 1: force the no-staging kernel
 int g_opt_ring_bytes = 0;      // 0: use all shared memory left
+int g_opt_no_batch = 0;        // 1: never take the tensor-core batch path
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
 
 int fail(int code, const char *fmt, ...) {
@@ -113,6 +115,8 @@ struct vsb_index {
     size_t prof_used = 0;
     size_t dev_bytes = 0;
     long long st_queries = 0, st_survivors = 0, st_fallbacks = 0, st_last_survivors = 0;
+    long long st_batches = 0, st_batch_cands = 0, st_batch_kept = 0;
+    void *batch = nullptr;   // BatchWs (tensor-core batch path workspace)
 };
 
 namespace {
@@ -430,6 +434,8 @@ int check_index(const vsb_index *ix) {
 
 }  // namespace
 
+#include "batch_host.inc"
+
 // ====================================================================== C ABI
 extern "C" {
 
@@ -462,6 +468,7 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "direct")) p = &g_opt_direct;
     else if (!strcmp(name, "ring_bytes")) p = &g_opt_ring_bytes;
     else if (!strcmp(name, "time_kernels")) p = &g_opt_time_kernels;
+    else if (!strcmp(name, "no_batch")) p = &g_opt_no_batch;
     if (!p) return fail(VSB_EINVAL, "unknown option %s", name);
     int old = *p;
     *p = value;
@@ -621,6 +628,9 @@ int64_t vsb_index_stat(const vsb_index *ix, const char *name) {
     if (!strcmp(name, "survivors")) return ix->st_survivors;
     if (!strcmp(name, "last_survivors")) return ix->st_last_survivors;
     if (!strcmp(name, "fallbacks")) return ix->st_fallbacks;
+    if (!strcmp(name, "batches")) return ix->st_batches;
+    if (!strcmp(name, "batch_cands")) return ix->st_batch_cands;
+    if (!strcmp(name, "batch_kept")) return ix->st_batch_kept;
     if (!strcmp(name, "fetch_bytes")) return (long long)(kResHdrBytes + sizeof(uint2) * kFirstFetch);
     if (!strcmp(name, "filter_blocks")) return (ix->num_sms * kWarps + kFilterWarps - 1) / kFilterWarps;
     return -1;
@@ -649,6 +659,7 @@ void vsb_index_free(vsb_index *ix) {
     if (ix->d_dist_all) cudaFree(ix->d_dist_all);
     if (ix->d_vec) cudaFree(ix->d_vec);
     for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
+    batch_free(ix);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -663,9 +674,16 @@ int vsb_scan_topk(vsb_index *ix, int metric, const void *queries, int nq, int k,
     }
     if (!out_rowids || !out_dist) return fail(VSB_EINVAL, "output buffers are null");
     const size_t qbytes = (size_t)ix->dim * ix->esize;
+    if (batch_supported(ix, metric, nq, k)) {   // tensor-core path; every query starts from a fresh cursor (max_index 0)
+        int rc = batch_scan(ix, metric, queries, nq, k, out_rowids, out_dist, out_counts);
+        if (rc == VSB_OK) return VSB_OK;
+        if (rc != VSB_ERANGE) return rc;
+        ix->st_fallbacks++;                      // capacity exceeded: per-query path below
+    }
     std::vector<uint2> cands;
     int mi = max_index ? *max_index : 0;
     for (int b = 0; b < nq; ++b) {
+        if (nq > 1) mi = 0;                      // batches: independent queries, like B separate cursors
         int rc = query_candidates(ix, metric, (const uint8_t *)queries + (size_t)b * qbytes, k, cands);
         if (rc) return rc;
         SlotState s{k, mi, out_dist + (size_t)b * k, out_rowids + (size_t)b * k};
@@ -679,7 +697,7 @@ int vsb_scan_topk(vsb_index *ix, int metric, const void *queries, int nq, int k,
         const int cnt = slots_finish(s);
         if (out_counts) out_counts[b] = cnt;
     }
-    if (max_index) *max_index = mi;
+    if (max_index && nq == 1) *max_index = mi;
     return VSB_OK;
 }
 

@@ -507,8 +507,25 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
 
     if constexpr (FAST) {
         // all stream lists -> shared memory, fully parallel and coalesced
-        for (int st = warp; st < fp.S; st += kFilterWarps)                  // one (padded) list per warp iteration, no division
-            slists[st * 32 + lane] = fp.lists[(size_t)st * kcap + lane];    // kcap == 32 on this path; entries >= k are -INF
+        {   // all S x 32 list values -> shared memory.  Loads are issued in independent batches: a naive copy loop
+            // serialises on the LDG -> STS dependency (generic pointers may alias) and cost ~1 us per iteration.
+            const float4 *src = reinterpret_cast<const float4 *>(fp.lists);  // kcap == 32 on this path: lists are contiguous
+            float4 *dst = reinterpret_cast<float4 *>(slists);
+            const int tot4 = fp.S * 8;
+            for (int base = 0; base < tot4; base += kFilterWarps * 32 * 4) {
+                float4 tmp[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * kFilterWarps * 32 + (int)threadIdx.x;
+                    tmp[u] = (i < tot4) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * kFilterWarps * 32 + (int)threadIdx.x;
+                    if (i < tot4) dst[i] = tmp[u];
+                }
+            }
+        }
         __syncthreads();
         if (warp < kSegments) {   // phase 1: warp g walks segment g in stream order, recording the running k-th value before each stream
             RegList L;
