@@ -107,11 +107,14 @@ VSB_API int vsb_replay_topk(const vsb_candidate *cands, int n, int k, int *max_i
 /* ---- device-resident variants used by bench.py (inputs already in HBM) --------------------- */
 /* runs the scan kernels for ONE query that is already in device memory (pitch-padded, see
  * vsb_index_query_pitch) and leaves the candidates in the engine's output buffer; no host copies. */
-VSB_API int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k);
+VSB_API int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k); /* returns the result slot (0/1) or <0 */
 /* blocks until the engine stream is idle and converts the last device-side result into top-k. */
 VSB_API int vsb_collect_last(vsb_index *ix, int k, int64_t *out_rowids, double *out_dist, int *out_count);
+/* same for a given result slot: two launches may be in flight (slots alternate), so query i+1 can be scanning while
+ * the host finishes query i */
+VSB_API int vsb_collect(vsb_index *ix, int slot, int k, int64_t *out_rowids, double *out_dist, int *out_count);
 VSB_API int vsb_index_query_pitch(const vsb_index *ix); /* bytes per query row on the device (multiple of 16) */
-/* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes","batches","batch_cands","batch_kept"}; -1 if unknown */
+/* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes","batches","batch_cands","batch_kept","tc_us","tc_rows","batch_us"}; -1 if unknown */
 VSB_API int64_t vsb_index_stat(const vsb_index *ix, const char *name);
 VSB_API void *vsb_index_stream(vsb_index *ix);           /* cudaStream_t of the engine, for event timing */
 /* kernel launch counter (all kernels launched by this library since load) */
@@ -119,7 +122,7 @@ VSB_API int64_t vsb_kernel_launches(void);
 /* with option "time_kernels"=1 every launch is bracketed by CUDA events on the engine stream; this returns
  * (and resets) the summed device time and launch count of the scan kernel and of the filter kernel. */
 VSB_API int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double *filter_ms, int *filter_launches);
-/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch"}; returns previous value */
+/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat"}; returns previous value */
 VSB_API int vsb_set_option(const char *name, int value);
 
 #ifdef __cplusplus

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "vsb_replay_topk": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "vsb_scan_device_query": (_i, [_vp, _i, _vp, _i]),
     "vsb_collect_last": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "vsb_collect": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "vsb_index_query_pitch": (_i, [_vp]),
     "vsb_index_stream": (_vp, [_vp]),
     "vsb_index_stat": (_i64, [_vp, C.c_char_p]),
@@ -183,8 +184,18 @@ class Index:
         self.eng.check(self.eng.lib.vsb_scan_candidates(self.h, metric, _ptr(q2), nq, k, _ptr(out), cap, _ptr(counts)))
         return [out[b, :counts[b]].copy() for b in range(nq)]
 
-    def scan_device_query(self, metric: int, d_query_ptr: int, k: int):
-        self.eng.check(self.eng.lib.vsb_scan_device_query(self.h, metric, d_query_ptr, k))
+    def scan_device_query(self, metric: int, d_query_ptr: int, k: int) -> int:
+        slot = self.eng.lib.vsb_scan_device_query(self.h, metric, d_query_ptr, k)
+        if slot < 0:
+            self.eng.check(slot)
+        return slot
+
+    def collect(self, slot: int, k: int):
+        ids = np.zeros(max(k, 1), dtype=np.int64)
+        dist = np.zeros(max(k, 1), dtype=np.float64)
+        cnt = C.c_int(0)
+        self.eng.check(self.eng.lib.vsb_collect(self.h, slot, k, _ptr(ids), _ptr(dist), C.byref(cnt)))
+        return ids[:cnt.value].copy(), dist[:cnt.value].copy()
 
     def stat(self, name: str) -> int:
         return int(self.eng.lib.vsb_index_stat(self.h, name.encode()))

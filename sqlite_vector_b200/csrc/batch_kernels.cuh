@@ -18,7 +18,7 @@ namespace vsb {
 
 enum { TK_BF16 = 0, TK_F16 = 1, TK_I8 = 2, TK_U8 = 3 };
 constexpr int kTcThreads = 256;     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue
-constexpr int kTcStages = 4;
+constexpr int kTcMaxStages = 8;
 constexpr int kTcM = 128;           // corpus rows per MMA tile
 constexpr int kTcKBytes = 128;      // one swizzle atom of K per stage
 
@@ -29,6 +29,7 @@ struct TcParams {
     int N;                  // MMA N: 32, 64, 128 or 256 queries per tile
     int NG;                 // query groups = ceil(nq / N)
     int KB;                 // 128-byte K blocks per row
+    int nstages;            // ring depth (2..kTcMaxStages)
     int mc;                 // MC_L2 / MC_COS / MC_DOT
     const float *qc;        // [NG*N] per-query constant (float, or int bit pattern for the integer kinds)
     const void *norms;      // [n] float (fp kinds) or int (integer kinds): sum of squares of each row
@@ -103,42 +104,95 @@ __host__ __device__ inline uint32_t umma_idesc(int kind, int N) {
 }
 
 // the per-element candidate test.  fp kinds use negated comparisons so that NaN scores count as hits.
-template <bool INT8>
-__device__ __forceinline__ bool tc_hit(int mc, uint32_t sbits, uint32_t qcbits, float rowf, int rowi) {
+template <bool INT8, int MC>
+__device__ __forceinline__ bool tc_hit(uint32_t sbits, uint32_t qcbits, float rowf, int rowi) {
     if constexpr (INT8) {
         const int s = (int)sbits;
-        if (mc == MC_DOT) return s > (int)qcbits;
-        if (mc == MC_L2) return (2 * s + rowi) >= (int)qcbits;                 // rowi = -|row|^2
-        return !(fmaf(-__uint_as_float(qcbits), rowf, (float)s) < 0.0f);       // cosine: rowf = |row|
+        if constexpr (MC == MC_DOT) return s > (int)qcbits;
+        else if constexpr (MC == MC_L2) return (2 * s + rowi) >= (int)qcbits;           // rowi = -|row|^2
+        else return !(fmaf(-__uint_as_float(qcbits), rowf, (float)s) < 0.0f);            // cosine: rowf = |row|
     } else {
         const float s = __uint_as_float(sbits), qc = __uint_as_float(qcbits);
-        if (mc == MC_DOT) return !(s <= qc);
-        if (mc == MC_L2) return !(fmaf(2.0f, s, rowf) <= qc);                  // rowf = -|row|^2 (1 - e)
-        return !(fmaf(-qc, rowf, s) < 0.0f);                                   // cosine: rowf = |row|
+        if constexpr (MC == MC_DOT) return !(s <= qc);
+        else if constexpr (MC == MC_L2) return !(fmaf(2.0f, s, rowf) <= qc);             // rowf = -|row|^2 (1 - e)
+        else return !(fmaf(-qc, rowf, s) < 0.0f);                                        // cosine: rowf = |row|
     }
 }
 
-template <int KIND>
+// issue a 32-column TMEM load without waiting (pair with tmem_wait_ld)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Tile order.  Streaming mode (BSTAT=false): tile t = corpus-tile * NG + query-group, both operands streamed through
+// the stage ring.  B-stationary mode (BSTAT=true, small K): the whole query group [N x K] is parked in shared memory and
+// the CTA sweeps its corpus tiles for that group, then moves to the next group — 3x less L2->SM traffic at dim 384 int8.
+struct TileIter {
+    long long mt0, ntm;   // first corpus tile, number of corpus tiles of the level
+    int NG, grid, bid, bstat;
+    long long per_cta;    // corpus tiles owned by this CTA (bstat)
+    long long count;      // tiles this CTA processes
+    __device__ __forceinline__ void init(const TcParams &p, int bstat_) {
+        mt0 = p.r0 / kTcM;
+        ntm = (p.r1 + kTcM - 1) / kTcM - mt0;
+        NG = p.NG; grid = gridDim.x; bid = blockIdx.x; bstat = bstat_;
+        if (bstat) {
+            per_cta = (ntm > bid) ? (ntm - bid + grid - 1) / grid : 0;
+            count = per_cta * NG;
+        } else {
+            const long long total = ntm * NG;
+            per_cta = 0;
+            count = (total > bid) ? (total - bid + grid - 1) / grid : 0;
+        }
+    }
+    __device__ __forceinline__ void at(long long tl, long long &mt, int &ng) const {
+        if (bstat) {
+            ng = (int)(tl / per_cta);
+            mt = mt0 + bid + (tl % per_cta) * grid;
+        } else {
+            const long long t = bid + tl * grid;
+            mt = mt0 + t / NG;
+            ng = (int)(t % NG);
+        }
+    }
+};
+
+template <int KIND, int MC, bool BSTAT>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, const TcParams prm) {
     constexpr bool INT8 = (KIND == TK_I8 || KIND == TK_U8);
     extern __shared__ __align__(1024) uint8_t tsm[];
-    const int N = prm.N;
-    const uint32_t a_bytes = kTcM * kTcKBytes, b_bytes = (uint32_t)N * kTcKBytes, stage_bytes = a_bytes + b_bytes;
-    uint8_t *stages = tsm;                                                     // [kTcStages][A | B], 1024-aligned
-    uint64_t *full = reinterpret_cast<uint64_t *>(tsm + kTcStages * stage_bytes);
-    uint64_t *empty = full + kTcStages;
-    uint64_t *tfull = empty + kTcStages;                                       // [2] accumulator ready
+    const int N = prm.N, NS = prm.nstages;
+    const uint32_t a_bytes = kTcM * kTcKBytes, b_bytes = (uint32_t)N * kTcKBytes;
+    const uint32_t stage_bytes = BSTAT ? a_bytes : a_bytes + b_bytes;
+    uint8_t *stages = tsm;                                                     // [NS][A (| B)], 1024-aligned
+    uint8_t *bsm = tsm + (size_t)NS * stage_bytes;                             // BSTAT: [KB][N x 128 B]
+    uint8_t *tail = bsm + (BSTAT ? (size_t)prm.KB * b_bytes : 0);
+    uint64_t *full = reinterpret_cast<uint64_t *>(tail);
+    uint64_t *empty = full + kTcMaxStages;
+    uint64_t *tfull = empty + kTcMaxStages;                                    // [2] accumulator ready
     uint64_t *tempty = tfull + 2;                                              // [2] accumulator drained
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *bfull = tempty + 2;                                              // BSTAT: query group landed / no longer read
+    uint64_t *bempty = bfull + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bempty + 1);
     uint32_t *qc_s = tmem_slot + 4;                                            // [NG*N]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_cols = (2 * N <= 32) ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kTcStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kTcMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(bfull, 1);
+        mbar_init(bempty, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
@@ -148,54 +202,68 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const long long mt0 = prm.r0 / kTcM, mt1 = (prm.r1 + kTcM - 1) / kTcM;    // corpus tiles of this level
-    const long long ntile = (mt1 - mt0) * prm.NG;                              // (corpus tile, query group) pairs, group fastest
+    TileIter ti;
+    ti.init(prm, BSTAT ? 1 : 0);
 
     if (warp == 0) {
         if (lane == 0) {                                                       // ===== TMA producer
             int it = 0;
-            for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
-                const long long mt = mt0 + t / prm.NG;
-                const int ng = (int)(t % prm.NG);
+            for (long long tl = 0; tl < ti.count; ++tl) {
+                long long mt; int ng;
+                ti.at(tl, mt, ng);
+                if constexpr (BSTAT) {
+                    if (tl % ti.per_cta == 0) {                                // new query group: park it in shared memory
+                        const int g = (int)(tl / ti.per_cta);
+                        mbar_wait(bempty, (uint32_t)((g & 1) ^ 1));
+                        mbar_expect_tx(bfull, (uint32_t)prm.KB * b_bytes);
+                        for (int kb = 0; kb < prm.KB; ++kb) tma_load_2d(bsm + (size_t)kb * b_bytes, &tmB, kb * kTcKBytes, ng * N, bfull);
+                    }
+                }
                 for (int kb = 0; kb < prm.KB; ++kb, ++it) {
-                    const int s = it % kTcStages;
-                    mbar_wait(&empty[s], (uint32_t)(((it / kTcStages) & 1) ^ 1));
+                    const int s = it % NS;
+                    mbar_wait(&empty[s], (uint32_t)(((it / NS) & 1) ^ 1));
                     mbar_expect_tx(&full[s], stage_bytes);
                     uint8_t *st = stages + (size_t)s * stage_bytes;
                     tma_load_2d(st, &tmA, kb * kTcKBytes, (int)(mt * kTcM), &full[s]);
-                    tma_load_2d(st + a_bytes, &tmB, kb * kTcKBytes, ng * N, &full[s]);
+                    if constexpr (!BSTAT) tma_load_2d(st + a_bytes, &tmB, kb * kTcKBytes, ng * N, &full[s]);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                                       // ===== MMA issuer (one thread)
             const uint32_t idesc = umma_idesc(KIND, N);
-            int it = 0, tl = 0;
-            for (long long t = blockIdx.x; t < ntile; t += gridDim.x, ++tl) {
-                const int as = tl & 1;
+            int it = 0;
+            for (long long tl = 0; tl < ti.count; ++tl) {
+                const int as = (int)(tl & 1);
+                if constexpr (BSTAT) {
+                    if (tl % ti.per_cta == 0) mbar_wait(bfull, (uint32_t)((tl / ti.per_cta) & 1));
+                }
                 mbar_wait(&tempty[as], (uint32_t)(((tl >> 1) & 1) ^ 1));
                 tc_fence_after();
                 for (int kb = 0; kb < prm.KB; ++kb, ++it) {
-                    const int s = it % kTcStages;
-                    mbar_wait(&full[s], (uint32_t)((it / kTcStages) & 1));
+                    const int s = it % NS;
+                    mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
                     tc_fence_after();
                     const uint8_t *st = stages + (size_t)s * stage_bytes;
-                    const uint64_t ad = umma_desc_sw128(st), bd = umma_desc_sw128(st + a_bytes);
+                    const uint64_t ad = umma_desc_sw128(st);
+                    const uint64_t bd = umma_desc_sw128(BSTAT ? bsm + (size_t)kb * b_bytes : st + a_bytes);
 #pragma unroll
                     for (int k4 = 0; k4 < kTcKBytes / 32; ++k4)                // UMMA_K = 32 bytes: advance start address by 2 (x16 B)
                         tc_mma<INT8>(tmem_base + (uint32_t)(as * N), ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idesc, (uint32_t)((kb | k4) != 0));
                     tc_commit(&empty[s]);                                      // frees the smem stage when these MMAs retire
                 }
                 tc_commit(&tfull[as]);                                         // accumulator complete
+                if constexpr (BSTAT) {
+                    if ((tl + 1) % ti.per_cta == 0) tc_commit(bempty);         // last tile of the group: B may be overwritten
+                }
             }
         }
     } else if (warp >= 4) {                                                    // ===== epilogue: TMEM -> registers -> threshold test
         const int quad = warp & 3;
-        int tl = 0;
-        for (long long t = blockIdx.x; t < ntile; t += gridDim.x, ++tl) {
-            const long long mt = mt0 + t / prm.NG;
-            const int ng = (int)(t % prm.NG);
-            const int as = tl & 1;
+        for (long long tl = 0; tl < ti.count; ++tl) {
+            long long mt; int ng;
+            ti.at(tl, mt, ng);
+            const int as = (int)(tl & 1);
             const long long row = mt * kTcM + quad * 32 + lane;
             const bool rowvalid = row >= prm.r0 && row < prm.r1;
             float rowf = 0.0f;
@@ -207,28 +275,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
                     rowf = (KIND == TK_U8) ? __fsqrt_rn((float)(uint32_t)nn) : __fsqrt_rn((float)nn);
                 } else {
                     const float nn = reinterpret_cast<const float *>(prm.norms)[row];
-                    rowf = (prm.mc == MC_L2) ? -nn * (1.0f - 1e-4f) : __fsqrt_rn(nn);
+                    rowf = (MC == MC_L2) ? -nn * (1.0f - 1e-4f) : __fsqrt_rn(nn);
                 }
             }
             mbar_wait(&tfull[as], (uint32_t)((tl >> 1) & 1));
             tc_fence_after();
-            for (int cb = 0; cb < N; cb += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * N + cb), v);
-                const uint32_t *qc = qc_s + ng * N + cb;
-                bool any = false;
+            // 64 accumulator columns per step: both TMEM loads are in flight before the single wait
+            for (int cb = 0; cb < N; cb += 64) {
+                uint32_t v[64];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * N + cb);
+                const bool two = (cb + 32) < N;
+                tmem_ld32_nowait(taddr, v);
+                if (two) tmem_ld32_nowait(taddr + 32, v + 32);
+                tmem_wait_ld();
+                const uint4 *qc4 = reinterpret_cast<const uint4 *>(qc_s + ng * N + cb);
+                bool any0 = false, any1 = false;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) any |= tc_hit<INT8>(prm.mc, v[j], qc[j], rowf, rowi);
-                any = any && rowvalid;
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const uint4 c = qc4[j4];
+                    any0 |= tc_hit<INT8, MC>(v[4 * j4 + 0], c.x, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 1], c.y, rowf, rowi) |
+                            tc_hit<INT8, MC>(v[4 * j4 + 2], c.z, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 3], c.w, rowf, rowi);
+                }
+                if (two) {
+#pragma unroll
+                    for (int j4 = 8; j4 < 16; ++j4) {
+                        const uint4 c = qc4[j4];
+                        any1 |= tc_hit<INT8, MC>(v[4 * j4 + 0], c.x, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 1], c.y, rowf, rowi) |
+                                tc_hit<INT8, MC>(v[4 * j4 + 2], c.z, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 3], c.w, rowf, rowi);
+                    }
+                }
+                const bool any = (any0 | any1) && rowvalid;
                 if (__ballot_sync(0xFFFFFFFFu, any)) {                         // rare: append (row, query) hits, one atomic per warp
-                    uint32_t mask = 0;
+                    const uint32_t *qc = qc_s + ng * N + cb;
+                    uint32_t mask0 = 0, mask1 = 0;
                     if (any) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mask |= (tc_hit<INT8>(prm.mc, v[j], qc[j], rowf, rowi) ? 1u : 0u) << j;
+                        for (int j = 0; j < 32; ++j) mask0 |= (tc_hit<INT8, MC>(v[j], qc[j], rowf, rowi) ? 1u : 0u) << j;
+                        if (two) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) mask1 |= (tc_hit<INT8, MC>(v[32 + j], qc[32 + j], rowf, rowi) ? 1u : 0u) << j;
+                        }
                         const int ncol = prm.nq - (ng * N + cb);                // padded query columns are never reported
-                        mask &= (ncol >= 32) ? 0xFFFFFFFFu : (ncol <= 0 ? 0u : ((1u << ncol) - 1u));
+                        mask0 &= (ncol >= 32) ? 0xFFFFFFFFu : (ncol <= 0 ? 0u : ((1u << ncol) - 1u));
+                        mask1 &= (ncol >= 64) ? 0xFFFFFFFFu : (ncol <= 32 ? 0u : ((1u << (ncol - 32)) - 1u));
                     }
-                    const int mine = __popc(mask);
+                    const int mine = __popc(mask0) + __popc(mask1);
                     int incl = mine;
                     for (int off = 1; off < 32; off <<= 1) {
                         const int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
@@ -239,11 +330,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
                     if (lane == 31) base = atomicAdd(prm.cand_count, (unsigned)total);
                     base = __shfl_sync(0xFFFFFFFFu, base, 31);
                     unsigned w = base + (unsigned)(incl - mine);
-                    while (mask) {
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int q = ng * N + cb + j;
-                        if (w < prm.cand_cap) prm.cand[w] = make_uint2((uint32_t)row, (uint32_t)q);
+                    while (mask0) {
+                        const int j = __ffs(mask0) - 1;
+                        mask0 &= mask0 - 1;
+                        if (w < prm.cand_cap) prm.cand[w] = make_uint2((uint32_t)row, (uint32_t)(ng * N + cb + j));
+                        ++w;
+                    }
+                    while (mask1) {
+                        const int j = __ffs(mask1) - 1;
+                        mask1 &= mask1 - 1;
+                        if (w < prm.cand_cap) prm.cand[w] = make_uint2((uint32_t)row, (uint32_t)(ng * N + cb + 32 + j));
                         ++w;
                     }
                 }
@@ -318,49 +414,93 @@ struct RefineParams {
     unsigned kept_cap;
 };
 
-// one warp per candidate: the reference distance with the arithmetic of the single-query kernel
+// eight lanes per candidate (four candidates per warp step): the reference distance with the arithmetic of the
+// single-query kernel; survivors are appended with ONE atomic per warp step (a single hot counter is the bottleneck
+// otherwise: 2.5 M same-address atomics per batch).
 template <int VT, int MC>
 __global__ void refine_kernel(const RefineParams rp) {
+    constexpr int G = 8;
     const unsigned ncand = min(*rp.cand_count, rp.cand_cap);
-    const int lane = threadIdx.x & 31;
-    const unsigned wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, sub = lane & (G - 1), grp = lane / G;
+    const unsigned wpb = blockDim.x >> 5, per_step = 32 / G;
     const int nc = rp.pitch / 16;
-    for (unsigned c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncand; c += gridDim.x * wpb) {
-        const uint2 cq = rp.cand[c];
+    const unsigned steps = (ncand + per_step - 1) / per_step;
+    for (unsigned st = blockIdx.x * wpb + (threadIdx.x >> 5); st < steps; st += gridDim.x * wpb) {
+        const unsigned c = st * per_step + grp;
+        const bool live = c < ncand;
+        uint2 cq = make_uint2(0, 0);
+        if (live) cq = rp.cand[c];
         const uint4 *rowp = reinterpret_cast<const uint4 *>(rp.vec + (size_t)cq.x * rp.pitch);
         const uint4 *qp = reinterpret_cast<const uint4 *>(rp.queries + (size_t)cq.y * rp.pitch);
         Accum A = {0.f, 0.f, 0.f, 0.f, 0, 0, 0};
         QueryNorm qn = {0.f, 0};
-        for (int i = lane; i < nc; i += 32) {
-            const uint4 rv = __ldg(rowp + i), qv = __ldg(qp + i);
-            accum16<VT, MC>(A, rv, qv);
-            if constexpr (VT == T_U8) {
-                qn.i = (int)__dp4a(qv.x, qv.x, (uint32_t)qn.i); qn.i = (int)__dp4a(qv.y, qv.y, (uint32_t)qn.i);
-                qn.i = (int)__dp4a(qv.z, qv.z, (uint32_t)qn.i); qn.i = (int)__dp4a(qv.w, qv.w, (uint32_t)qn.i);
-            } else if constexpr (VT == T_I8) {
-                qn.i = __dp4a((int)qv.x, (int)qv.x, qn.i); qn.i = __dp4a((int)qv.y, (int)qv.y, qn.i);
-                qn.i = __dp4a((int)qv.z, (int)qv.z, qn.i); qn.i = __dp4a((int)qv.w, (int)qv.w, qn.i);
-            } else if constexpr (MC == MC_COS) {
-                float x[8];
-                unpack8<VT>(qv, x);
+        if (live) {
+            for (int i = sub; i < nc; i += G) {
+                const uint4 rv = __ldg(rowp + i), qv = __ldg(qp + i);
+                accum16<VT, MC>(A, rv, qv);
+                if constexpr (VT == T_U8) {
+                    qn.i = (int)__dp4a(qv.x, qv.x, (uint32_t)qn.i); qn.i = (int)__dp4a(qv.y, qv.y, (uint32_t)qn.i);
+                    qn.i = (int)__dp4a(qv.z, qv.z, (uint32_t)qn.i); qn.i = (int)__dp4a(qv.w, qv.w, (uint32_t)qn.i);
+                } else if constexpr (VT == T_I8) {
+                    qn.i = __dp4a((int)qv.x, (int)qv.x, qn.i); qn.i = __dp4a((int)qv.y, (int)qv.y, qn.i);
+                    qn.i = __dp4a((int)qv.z, (int)qv.z, qn.i); qn.i = __dp4a((int)qv.w, (int)qv.w, qn.i);
+                } else if constexpr (MC == MC_COS) {
+                    float x[8];
+                    unpack8<VT>(qv, x);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) qn.f = fmaf(x[j], x[j], qn.f);
+                    for (int j = 0; j < 8; ++j) qn.f = fmaf(x[j], x[j], qn.f);
+                }
             }
         }
-        accum_reduce(A, 32);
-        for (int off = 16; off >= 1; off >>= 1) {
+        accum_reduce(A, G);
+        for (int off = G / 2; off >= 1; off >>= 1) {
             qn.f += __shfl_xor_sync(0xFFFFFFFFu, qn.f, off);
             qn.i += __shfl_xor_sync(0xFFFFFFFFu, qn.i, off);
         }
         const float d = finalize<VT, MC>(A, qn, rp.root);
-        if (lane == 0 && d < rp.U[cq.y]) {
-            const unsigned w = atomicAdd(rp.kept_count, 1u);
-            if (w < rp.kept_cap) {
-                rp.kept_key[w] = ((unsigned long long)cq.y << 32) | cq.x;
-                rp.kept_val[w] = d;
+        const bool keep = live && sub == 0 && d < rp.U[cq.y];
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+        if (m) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(rp.kept_count, (unsigned)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (keep) {
+                const unsigned w = base + __popc(m & ((1u << lane) - 1u));
+                if (w < rp.kept_cap) {
+                    rp.kept_key[w] = ((unsigned long long)cq.y << 32) | cq.x;
+                    rp.kept_val[w] = d;
+                }
             }
         }
     }
+}
+
+// final exchange sort of each query's slots, literally the loop of vFullScanSortSlots (src/sqlite-vector.c:2057-2065):
+// one thread per query, its k slots staged in shared memory.  Unused slots stay +INF and sort to the end.
+__global__ void final_sort_kernel(float *slot_d, unsigned *slot_row, int nq, int k, int kcap) {
+    extern __shared__ __align__(16) uint8_t fsm2[];
+    const int stride = k | 1;                                        // odd stride: conflict-free per-thread rows
+    float *sd = reinterpret_cast<float *>(fsm2) + (size_t)threadIdx.x * stride;
+    unsigned *sr = reinterpret_cast<unsigned *>(reinterpret_cast<float *>(fsm2) + (size_t)blockDim.x * stride) + (size_t)threadIdx.x * stride;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    float *gd = slot_d + (size_t)q * kcap;
+    unsigned *gr = slot_row + (size_t)q * kcap;
+    for (int j = 0; j < k; ++j) { sd[j] = gd[j]; sr[j] = gr[j]; }
+    for (int i = 0; i + 1 < k; ++i) {
+        float di = sd[i];
+        unsigned ri = sr[i];
+        for (int j = i + 1; j < k; ++j) {
+            const float dj = sd[j];
+            if (dj < di) {
+                const unsigned rj = sr[j];
+                sd[j] = di; sr[j] = ri;
+                di = dj; ri = rj;
+            }
+        }
+        sd[i] = di; sr[i] = ri;
+    }
+    for (int j = 0; j < k; ++j) { gd[j] = sd[j]; gr[j] = sr[j]; }
 }
 
 // per-query slot state carried across levels (the reference's cursor arrays, src/sqlite-vector.c:1808-1813)

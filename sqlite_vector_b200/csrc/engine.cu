@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -34,6 +35,8 @@ int g_opt_stage_bytes = 8192;  // target bytes of one warp tile (ring stage)
 int g_opt_direct = 0;          // 1: force the no-staging kernel
 int g_opt_ring_bytes = 0;      // 0: use all shared memory left
 int g_opt_no_batch = 0;        // 1: never take the tensor-core batch path
+int g_opt_batch_debug = 0;     // 1: print per-stage timings of the batch path to stderr (serialises the stages)
+int g_opt_bstat = 0;           // 1: park the query group in shared memory when it fits (measured: no gain, off by default)
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
 
 int fail(int code, const char *fmt, ...) {
@@ -83,6 +86,7 @@ struct Slot {
     int *h_hdr = nullptr, *d_hdr = nullptr;
     uint8_t *h_query = nullptr, *d_query = nullptr;  // pinned staging + device copy of the query
     int *d_ctrl = nullptr;
+    cudaEvent_t done = nullptr;   // recorded after the result block of this slot has been copied to the host
     int seq = 0;
     int nblocks = 0;
 };
@@ -115,7 +119,7 @@ struct vsb_index {
     size_t prof_used = 0;
     size_t dev_bytes = 0;
     long long st_queries = 0, st_survivors = 0, st_fallbacks = 0, st_last_survivors = 0;
-    long long st_batches = 0, st_batch_cands = 0, st_batch_kept = 0;
+    long long st_batches = 0, st_batch_cands = 0, st_batch_kept = 0, st_tc_us = 0, st_tc_rows = 0, st_batch_us = 0;
     void *batch = nullptr;   // BatchWs (tensor-core batch path workspace)
 };
 
@@ -204,6 +208,7 @@ int ensure_slots(vsb_index *ix) {
         CU(cudaMalloc((void **)&s.d_query, (size_t)ix->pitch));
         CU(cudaMalloc((void **)&s.d_ctrl, sizeof(int) * 4));
         CU(cudaMemset(s.d_ctrl, 0, sizeof(int) * 4));
+        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
     ix->slots_ready = true;
     return VSB_OK;
@@ -305,6 +310,7 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         if (pev) CU(cudaEventRecord(pev[2], ix->stream));
         if (nblocks > kTableCap) return fail(VSB_ERANGE, "too many filter blocks (%d)", nblocks);
         CU(cudaMemcpyAsync(slot->h_res, slot->d_res, kResHdrBytes + sizeof(uint2) * kFirstFetch, cudaMemcpyDeviceToHost, ix->stream));
+        CU(cudaEventRecord(slot->done, ix->stream));
     }
     return VSB_OK;
 }
@@ -469,6 +475,8 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "ring_bytes")) p = &g_opt_ring_bytes;
     else if (!strcmp(name, "time_kernels")) p = &g_opt_time_kernels;
     else if (!strcmp(name, "no_batch")) p = &g_opt_no_batch;
+    else if (!strcmp(name, "bstat")) p = &g_opt_bstat;
+    else if (!strcmp(name, "batch_debug")) p = &g_opt_batch_debug;
     if (!p) return fail(VSB_EINVAL, "unknown option %s", name);
     int old = *p;
     *p = value;
@@ -631,6 +639,9 @@ int64_t vsb_index_stat(const vsb_index *ix, const char *name) {
     if (!strcmp(name, "batches")) return ix->st_batches;
     if (!strcmp(name, "batch_cands")) return ix->st_batch_cands;
     if (!strcmp(name, "batch_kept")) return ix->st_batch_kept;
+    if (!strcmp(name, "tc_us")) return ix->st_tc_us;
+    if (!strcmp(name, "batch_us")) return ix->st_batch_us;
+    if (!strcmp(name, "tc_rows")) return ix->st_tc_rows;
     if (!strcmp(name, "fetch_bytes")) return (long long)(kResHdrBytes + sizeof(uint2) * kFirstFetch);
     if (!strcmp(name, "filter_blocks")) return (ix->num_sms * kWarps + kFilterWarps - 1) / kFilterWarps;
     return -1;
@@ -652,6 +663,7 @@ void vsb_index_free(vsb_index *ix) {
         if (s.h_query) cudaFreeHost(s.h_query);
         if (s.d_query) cudaFree(s.d_query);
         if (s.d_ctrl) cudaFree(s.d_ctrl);
+        if (s.done) cudaEventDestroy(s.done);
     }
     if (ix->d_lists) cudaFree(ix->d_lists);
     if (ix->d_logs) cudaFree(ix->d_logs);
@@ -675,7 +687,9 @@ int vsb_scan_topk(vsb_index *ix, int metric, const void *queries, int nq, int k,
     if (!out_rowids || !out_dist) return fail(VSB_EINVAL, "output buffers are null");
     const size_t qbytes = (size_t)ix->dim * ix->esize;
     if (batch_supported(ix, metric, nq, k)) {   // tensor-core path; every query starts from a fresh cursor (max_index 0)
+        const auto t0 = std::chrono::steady_clock::now();
         int rc = batch_scan(ix, metric, queries, nq, k, out_rowids, out_dist, out_counts);
+        ix->st_batch_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
         if (rc == VSB_OK) return VSB_OK;
         if (rc != VSB_ERANGE) return rc;
         ix->st_fallbacks++;                      // capacity exceeded: per-query path below
@@ -792,17 +806,23 @@ int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k)
     if (rc) return rc;
     ix->last_slot = si;
     ix->last_metric = metric;
-    return VSB_OK;
+    return si;   // slot id (>= 0) for vsb_collect
 }
 
 int vsb_collect_last(vsb_index *ix, int k, int64_t *out_rowids, double *out_dist, int *out_count) {
     if (check_index(ix)) return VSB_EINVAL;
     if (ix->last_slot < 0) return fail(VSB_EINVAL, "no device scan was launched");
+    return vsb_collect(ix, ix->last_slot, k, out_rowids, out_dist, out_count);
+}
+
+int vsb_collect(vsb_index *ix, int slot_id, int k, int64_t *out_rowids, double *out_dist, int *out_count) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (slot_id < 0 || slot_id >= kSlots || !ix->slots_ready) return fail(VSB_EINVAL, "bad slot");
     CU(cudaSetDevice(ix->device));
-    CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaEventSynchronize(ix->slot[slot_id].done));   // only this query's result; a later launch may still be running
     std::vector<uint2> cands;
     bool overflow = false;
-    int n = gather_survivors(ix, &ix->slot[ix->last_slot], cands, &overflow);
+    int n = gather_survivors(ix, &ix->slot[slot_id], cands, &overflow);
     if (n < 0) return n;
     if (overflow) return fail(VSB_ERANGE, "candidate log overflowed; use vsb_scan_topk (host query) for this input");
     SlotState s{k, 0, out_dist, out_rowids};
