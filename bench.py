@@ -152,7 +152,28 @@ def cpu_reference_run(buf, n, dim, k, queries_i8: np.ndarray, threads: int, reps
 
 
 # ------------------------------------------------------------------ main
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly one JSON line: route everything else (NCCL banners, library prints) to stderr"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
@@ -238,7 +259,13 @@ def main():
         # sharded: every rank scans its rows, candidates are all-gathered, the slot algorithm is replayed
         raise RuntimeError("unreachable")
 
+    exch = shard.DeviceExchange(ix, eng, world, bounds, device) if world > 1 else None
+
     def step_sharded(i):
+        # scan + filter on every rank, device-side all-gather of the result blocks, one D2H, C merge (slot replay)
+        return exch.query(api.L2, q_dev[i].data_ptr(), k)
+
+    def step_sharded_host(i):   # reference-facing path: host query in, candidates out, gather, replay
         c = ix.scan_candidates(api.L2, q_host[i], k, cap)[0]
         return shard.sharded_topk(eng, c, k, cap, device)[:2]
 
@@ -272,8 +299,14 @@ def main():
             pending = slot
         last = ix.collect(pending, k)
     else:
+        # sharded: two queries in flight as well — the exchange + merge of query i overlaps the scan of query i+1
+        pending = None
         for i in range(K):
-            last = run(W + i)
+            t = exch.submit(api.L2, q_dev[W + i].data_ptr(), k)
+            if pending is not None:
+                last = exch.finish(pending)
+            pending = t
+        last = exch.finish(pending)
     e1.record(st)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -299,7 +332,7 @@ def main():
 
     # ---- e2e: host query in, host top-k out, through the public C-ABI call
     for i in range(W):
-        (ix.scan_topk(api.L2, q_host[i], k) if world == 1 else step_sharded(i))
+        (ix.scan_topk(api.L2, q_host[i], k) if world == 1 else step_sharded_host(i))
     barrier()
     t0 = time.perf_counter()
     surv0, q0 = ix.stat("survivors"), ix.stat("queries")
@@ -307,7 +340,7 @@ def main():
         if world == 1:
             ix.scan_topk(api.L2, q_host[W + i], k)
         else:
-            step_sharded(W + i)
+            step_sharded_host(W + i)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -343,7 +376,7 @@ def main():
         "config": {"workload": workload, "metric": "L2", "k": k, "batch": 1, "rows": n, "dim": dim, "shards": world,
                    "l2_flush": "none needed: each step streams the whole shard (%.2f GB) which exceeds the 126 MB L2" % (shard_bytes / 1e9),
                    "result_mode": "exact reference slot replay (bit-exact rowids/order/distances vs distance-cpu.c)",
-                   "in_flight": 2 if world == 1 else 1},
+                   "in_flight": 2},
         "e2e": {"value": K / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(pitch),
                 "d2h_bytes_per_step": d2h_bytes, "avg_candidates_per_query": avg_surv,
                 "note": "vsb_scan_topk: pinned query H2D + scan/filter kernels + one D2H copy of the candidate block (header + table + 1024 slots) + host slot replay"},
@@ -390,7 +423,7 @@ def main():
                                    "gpu_result_matches_reference": chk}
         except MemoryError as ex:
             out["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": cores, "kind": "reference", "sample": f"skipped: {ex}"}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -467,7 +500,7 @@ def reference_arm(torch, a, n, dim, k, K, W, workload, cores):
                             "sample": f"{K} steps x {cores} queries over the {n}x{dim} preload buffer"},
            "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 if __name__ == "__main__":

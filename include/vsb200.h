@@ -113,6 +113,13 @@ VSB_API int vsb_collect_last(vsb_index *ix, int k, int64_t *out_rowids, double *
 /* same for a given result slot: two launches may be in flight (slots alternate), so query i+1 can be scanning while
  * the host finishes query i */
 VSB_API int vsb_collect(vsb_index *ix, int slot, int k, int64_t *out_rowids, double *out_dist, int *out_count);
+/* device address and size of a slot's result block (header + block table + first candidates) so that a launcher
+ * can all-gather the shards' blocks on the device (NCCL) without a host round trip */
+VSB_API int vsb_result_block(vsb_index *ix, int slot, void **d_block, int64_t *bytes);
+/* host-side merge of `world` gathered result blocks (block r starts at blocks + r*block_stride) into the reference's
+ * top-k; rows are numbered first_seq[r] + local and rowids are implicit (global row + 1).  Returns the row count. */
+VSB_API int vsb_merge_result_blocks(const void *blocks, int world, int64_t block_stride, const int64_t *first_seq, int k,
+                                    int64_t *out_rowids, double *out_dist);
 VSB_API int vsb_index_query_pitch(const vsb_index *ix); /* bytes per query row on the device (multiple of 16) */
 /* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes","batches","batch_cands","batch_kept","tc_us","tc_rows","batch_us"}; -1 if unknown */
 VSB_API int64_t vsb_index_stat(const vsb_index *ix, const char *name);

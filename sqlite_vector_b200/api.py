@@ -45,6 +45,8 @@ _SIGNATURES = {
     "vsb_scan_device_query": (_i, [_vp, _i, _vp, _i]),
     "vsb_collect_last": (_i, [_vp, _i, _vp, _vp, _vp]),
     "vsb_collect": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "vsb_result_block": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i64)]),
+    "vsb_merge_result_blocks": (_i, [_vp, _i, _i64, _vp, _i, _vp, _vp]),
     "vsb_index_query_pitch": (_i, [_vp]),
     "vsb_index_stream": (_vp, [_vp]),
     "vsb_index_stat": (_i64, [_vp, C.c_char_p]),
@@ -89,6 +91,15 @@ class Engine:
 
     def set_option(self, name: str, value: int) -> int:
         return self.lib.vsb_set_option(name.encode(), int(value))
+
+    def merge_result_blocks(self, blocks: np.ndarray, world: int, stride: int, first_seq: np.ndarray, k: int):
+        ids = np.zeros(max(k, 1), dtype=np.int64)
+        dist = np.zeros(max(k, 1), dtype=np.float64)
+        fs = np.ascontiguousarray(first_seq, dtype=np.int64)
+        cnt = self.lib.vsb_merge_result_blocks(_ptr(blocks), world, stride, _ptr(fs), k, _ptr(ids), _ptr(dist))
+        if cnt < 0:
+            self.check(cnt)
+        return ids[:cnt], dist[:cnt]
 
     def replay_topk(self, cands: np.ndarray, k: int, max_index: int = 0):
         cands = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
@@ -189,6 +200,12 @@ class Index:
         if slot < 0:
             self.eng.check(slot)
         return slot
+
+    def result_block(self, slot: int):
+        """(device pointer, bytes) of the slot's result block"""
+        ptr, nbytes = _vp(), _i64()
+        self.eng.check(self.eng.lib.vsb_result_block(self.h, slot, C.byref(ptr), C.byref(nbytes)))
+        return int(ptr.value), int(nbytes.value)
 
     def collect(self, slot: int, k: int):
         ids = np.zeros(max(k, 1), dtype=np.int64)

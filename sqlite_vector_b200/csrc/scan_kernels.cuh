@@ -270,6 +270,30 @@ __device__ __forceinline__ void list_argmax(const float *list, int kcap, int lan
     pos = __shfl_sync(0xFFFFFFFFu, bi, src);
 }
 
+// bitonic sort of one value per lane, ascending by lane
+__device__ __forceinline__ float warp_sort_asc(float v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+            const float o = __shfl_xor_sync(0xFFFFFFFFu, v, stride);
+            const bool up = ((lane & size) == 0);            // ascending block?
+            const bool lower = ((lane & stride) == 0);
+            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
+        }
+    }
+    return v;
+}
+// v is a bitonic sequence across the lanes -> ascending
+__device__ __forceinline__ float warp_bitonic_merge_asc(float v, int lane) {
+#pragma unroll
+    for (int stride = 16; stride >= 1; stride >>= 1) {
+        const float o = __shfl_xor_sync(0xFFFFFFFFu, v, stride);
+        v = ((lane & stride) == 0) ? fminf(v, o) : fmaxf(v, o);
+    }
+    return v;
+}
+
 // ------------------------------------------------------------------ the scan kernel
 template <int VT, int MC, bool DIRECT>
 __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm) {
@@ -416,7 +440,14 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
     if (topk) {
         __syncwarp();
         float *gl = prm.lists + (size_t)sidx * prm.kcap;
-        for (int j = lane; j < prm.kcap; j += 32) gl[j] = mylist[j];
+        if (prm.kcap == 32) {
+            // k <= 32: publish the list sorted ascending, +INF padded (filter_kernel merges sorted lists in registers)
+            float v = (lane < prm.k) ? mylist[lane] : INFINITY;
+            v = warp_sort_asc(v, lane);
+            gl[lane] = v;
+        } else {
+            for (int j = lane; j < prm.kcap; j += 32) gl[j] = mylist[j];
+        }
         if (lane == 0) {
             prm.counts[sidx] = logged;
             if (logged > prm.logcap) atomicExch(&prm.ctrl[1], 1);
@@ -453,27 +484,38 @@ __device__ __forceinline__ float funkey(uint32_t k) {  // inverse of fkey
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
-// k <= 32: the warp's k-list lives in one register per lane (lanes >= k hold -INF and never win the max)
-struct RegList {
+// k <= 32: the warp's k-list lives in one register per lane, SORTED ascending (lanes >= k hold +INF); the running
+// k-th value is lane k-1.  Incoming lists are sorted too (scan_kernel publishes them that way), so an offer is either
+// a couple of shift-inserts or one bitonic merge — no serial chain of k inserts for the first streams of a segment.
+struct SortedList {
     float v, thr;
-    int pos;
-    __device__ __forceinline__ void init(int lane, int k) { v = (lane < k) ? INFINITY : -INFINITY; thr = INFINITY; pos = 0; }
-    __device__ __forceinline__ void insert(int lane, float dv) {
-        if (lane == pos) v = dv;
-        const uint32_t key = fkey(v);
-        const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, key);
-        pos = __ffs(__ballot_sync(0xFFFFFFFFu, key == mx)) - 1;
-        thr = funkey(mx);
+    int k;
+    __device__ __forceinline__ void init(int lane, int k_) { k = k_; v = INFINITY; thr = INFINITY; }
+    __device__ __forceinline__ void insert(int lane, float dv) {           // dv < thr
+        const int pos = __popc(__ballot_sync(0xFFFFFFFFu, v <= dv));       // elements that stay in front of dv
+        const float up = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+        v = (lane < pos) ? v : (lane == pos ? dv : up);
+        if (lane >= k) v = INFINITY;
+        thr = __shfl_sync(0xFFFFFFFFu, v, k - 1);
     }
-    // offer the (<= 32) values held one per lane, in lane order
-    __device__ __forceinline__ void offer(int lane, float val) {
-        unsigned m = __ballot_sync(0xFFFFFFFFu, val < thr);
-        while (m) {
-            const int sl = __ffs(m) - 1;
-            m &= m - 1;
-            const float dv = __shfl_sync(0xFFFFFFFFu, val, sl);
-            if (dv < thr) insert(lane, dv);
+    // val: a sorted ascending list, one value per lane, +INF padded
+    __device__ __forceinline__ void offer_sorted(int lane, float val) {
+        const int cnt = __popc(__ballot_sync(0xFFFFFFFFu, val < thr));     // these are the first cnt lanes
+        if (cnt == 0) return;
+        if (cnt <= 2) {
+            const float a = __shfl_sync(0xFFFFFFFFu, val, 0);
+            insert(lane, a);
+            if (cnt == 2) {
+                const float b = __shfl_sync(0xFFFFFFFFu, val, 1);
+                if (b < thr) insert(lane, b);
+            }
+            return;
         }
+        // 32 smallest of the 64 values: min(L[i], R[31-i]) is bitonic; one merge network sorts it
+        const float rev = __shfl_sync(0xFFFFFFFFu, val, 31 - lane);
+        v = warp_bitonic_merge_asc(fminf(v, rev), lane);
+        if (lane >= k) v = INFINITY;
+        thr = __shfl_sync(0xFFFFFFFFu, v, k - 1);
     }
 };
 
@@ -528,20 +570,20 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
         }
         __syncthreads();
         if (warp < kSegments) {   // phase 1: warp g walks segment g in stream order, recording the running k-th value before each stream
-            RegList L;
+            SortedList L;
             L.init(lane, k);
             const int s0 = warp * G, s1 = min(fp.S, s0 + G);
             for (int st = s0; st < s1; ++st) {
                 if (lane == 0) tlocal[st] = L.thr;
-                L.offer(lane, (lane < k) ? slists[st * 32 + lane] : INFINITY);
+                L.offer_sorted(lane, slists[st * 32 + lane]);
             }
             seglist[warp * kcap + lane] = L.v;
         }
         __syncthreads();
         if (warp < kSegments) {   // phase 2: warp g merges the lists of segments 0..g-1
-            RegList L;
+            SortedList L;
             L.init(lane, k);
-            for (int g = 0; g < warp; ++g) L.offer(lane, (lane < k) ? seglist[g * kcap + lane] : INFINITY);
+            for (int g = 0; g < warp; ++g) L.offer_sorted(lane, seglist[g * kcap + lane]);
             if (lane == 0) tseg[warp] = L.thr;
         }
         __syncthreads();
@@ -656,6 +698,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
             fp.hdr[0] = total;
             fp.hdr[1] = (ovf != 0 || total > fp.outcap) ? 1 : 0;
             fp.hdr[2] = fp.seqno;
+            fp.hdr[3] = (int)gridDim.x;
             fp.ctrl[0] = 0; fp.ctrl[1] = 0; fp.ctrl[2] = 0;
         }
     }

@@ -134,3 +134,33 @@ def test_sharded_merge_gloo_world2(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29613", str(script), ROOT], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and "SHARD_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_merge_result_blocks_matches_oracle(oracle):
+    """vsb_merge_result_blocks (host) over hand-built shard result blocks == the oracle's scan of the whole column"""
+    import sqlite_vector_b200 as vs
+    eng = vs.load_engine()
+    rng = np.random.Generator(np.random.PCG64(17))
+    n, dim, k, world = 1500, 8, 20, 3
+    x = rng.integers(-3, 4, (n, dim)).astype(np.int8)
+    q = rng.integers(-3, 4, dim).astype(np.int8)
+    bounds = [0, 400, 1100, n]
+    HDR, TABLE, FIRST = 64, 512 * 8, 1024
+    stride = HDR + TABLE + FIRST * 8
+    blocks = np.zeros(world * stride, dtype=np.uint8)
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        diff = x[lo:hi].astype(np.int32) - q.astype(np.int32)
+        d = np.sqrt((diff * diff).sum(1).astype(np.float32))
+        blk = blocks[r * stride:(r + 1) * stride]
+        hdr = blk[:HDR].view(np.int32)
+        hdr[0], hdr[1], hdr[2], hdr[3] = hi - lo, 0, 1, 2            # total, overflow, seq, filter blocks
+        table = blk[HDR:HDR + TABLE].view(np.int32).reshape(-1, 2)
+        half = (hi - lo) // 2
+        table[0] = (0, half); table[1] = (half, hi - lo - half)      # two "filter blocks", contiguous in scan order
+        out = blk[HDR + TABLE:].view(np.uint32).reshape(-1, 2)
+        out[:hi - lo, 0] = d.view(np.uint32)
+        out[:hi - lo, 1] = np.arange(hi - lo, dtype=np.uint32)
+    ids, dist = eng.merge_result_blocks(blocks, world, stride, np.array(bounds[:world]), k)
+    want_ids, want_d = oracle.scan_dense(po.L2, po.I8, q, x, np.arange(1, n + 1, dtype=np.int64), k)
+    assert np.array_equal(ids, want_ids) and np.array_equal(dist, want_d)
