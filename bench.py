@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU reference leg (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the batch=1024 tensor-core extras")
+    ap.add_argument("--engine-opt", action="append", default=[], help="name=value passed to vsb_set_option (experiments)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -217,6 +218,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     eng = vs.load_engine()
+    for kv in a.engine_opt:
+        name, val = kv.split("=")
+        eng.set_option(name, int(val))
 
     # ---- resident corpus shard (preload is outside the timed region, like the reference's preloaded buffer)
     bounds = shard.shard_bounds(n, world)

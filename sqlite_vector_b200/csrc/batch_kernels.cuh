@@ -280,14 +280,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
             }
             mbar_wait(&tfull[as], (uint32_t)((tl >> 1) & 1));
             tc_fence_after();
-            // 64 accumulator columns per step: both TMEM loads are in flight before the single wait
-            for (int cb = 0; cb < N; cb += 64) {
-                uint32_t v[64];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * N + cb);
+            // 64 accumulator columns per step, software pipelined: the TMEM loads of step i+1 are in flight while step i
+            // is tested (TMEM reads are 64 B/clk/SM: 128x256 fp32 accumulators take >= 2048 clk to drain, which bounds
+            // small-K tiles; keeping the read pipe busy is what matters here).
+            const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * N);
+            auto issue = [&](int cb, uint32_t *v) {
+                tmem_ld32_nowait(tbase + (uint32_t)cb, v);
+                if (cb + 32 < N) tmem_ld32_nowait(tbase + (uint32_t)cb + 32, v + 32);
+            };
+            auto process = [&](int cb, const uint32_t *v) {
                 const bool two = (cb + 32) < N;
-                tmem_ld32_nowait(taddr, v);
-                if (two) tmem_ld32_nowait(taddr + 32, v + 32);
-                tmem_wait_ld();
                 const uint4 *qc4 = reinterpret_cast<const uint4 *>(qc_s + ng * N + cb);
                 bool any0 = false, any1 = false;
 #pragma unroll
@@ -342,6 +344,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
                         if (w < prm.cand_cap) prm.cand[w] = make_uint2((uint32_t)row, (uint32_t)(ng * N + cb + 32 + j));
                         ++w;
                     }
+                }
+            };
+            uint32_t va[64], vb[64];
+            issue(0, va);
+            for (int cb = 0; cb < N; cb += 128) {
+                tmem_wait_ld();
+                if (cb + 64 < N) issue(cb + 64, vb);
+                process(cb, va);
+                if (cb + 64 < N) {
+                    tmem_wait_ld();
+                    if (cb + 128 < N) issue(cb + 128, va);
+                    process(cb + 64, vb);
                 }
             }
             tc_fence_before();
