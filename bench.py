@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU reference leg (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the batch=1024 tensor-core extras")
+    ap.add_argument("--group", type=int, default=4, help="sharded runs: queries per exchange group (two groups in flight)")
     ap.add_argument("--engine-opt", action="append", default=[], help="name=value passed to vsb_set_option (experiments)")
     a = ap.parse_args()
 
@@ -263,15 +264,27 @@ def main():
         # sharded: every rank scans its rows, candidates are all-gathered, the slot algorithm is replayed
         raise RuntimeError("unreachable")
 
-    exch = shard.DeviceExchange(ix, eng, world, bounds, device) if world > 1 else None
+    exch = shard.DeviceExchange(ix, eng, world, bounds, device, group=a.group) if world > 1 else None
+    G = exch.group if exch else 1
 
     def step_sharded(i):
         # scan + filter on every rank, device-side all-gather of the result blocks, one D2H, C merge (slot replay)
         return exch.query(api.L2, q_dev[i].data_ptr(), k)
 
-    def step_sharded_host(i):   # reference-facing path: host query in, candidates out, gather, replay
-        c = ix.scan_candidates(api.L2, q_host[i], k, cap)[0]
-        return shard.sharded_topk(eng, c, k, cap, device)[:2]
+    def run_sharded(first, count, on_device):
+        """`count` independent queries through the grouped exchange, two groups in flight: the all-gather + merge of
+        group g overlaps the scans of group g+1.  on_device=False: host queries (pinned H2D inside the call)."""
+        pending, last_res = None, None
+        for g0 in range(0, count, G):
+            idx = range(first + g0, first + min(count, g0 + G))
+            qs = [q_dev[i].data_ptr() for i in idx] if on_device else [q_host[i] for i in idx]
+            t = exch.submit(api.L2, qs, k, on_device=on_device)
+            if pending is not None:
+                last_res = exch.finish(pending)[-1]
+            pending = t
+        if pending is not None:
+            last_res = exch.finish(pending)[-1]
+        return last_res
 
     def barrier():
         if world > 1:
@@ -303,14 +316,7 @@ def main():
             pending = slot
         last = ix.collect(pending, k)
     else:
-        # sharded: two queries in flight as well — the exchange + merge of query i overlaps the scan of query i+1
-        pending = None
-        for i in range(K):
-            t = exch.submit(api.L2, q_dev[W + i].data_ptr(), k)
-            if pending is not None:
-                last = exch.finish(pending)
-            pending = t
-        last = exch.finish(pending)
+        last = run_sharded(W, K, True)
     e1.record(st)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -335,16 +341,20 @@ def main():
         lat_ms = (time.perf_counter() - t0l) / min(K, 100) * 1e3
 
     # ---- e2e: host query in, host top-k out, through the public C-ABI call
-    for i in range(W):
-        (ix.scan_topk(api.L2, q_host[i], k) if world == 1 else step_sharded_host(i))
+    if world == 1:
+        for i in range(W):
+            ix.scan_topk(api.L2, q_host[i], k)
+    else:
+        run_sharded(0, W, False)
     barrier()
     t0 = time.perf_counter()
     surv0, q0 = ix.stat("survivors"), ix.stat("queries")
-    for i in range(K):
-        if world == 1:
+    if world == 1:
+        for i in range(K):
             ix.scan_topk(api.L2, q_host[W + i], k)
-        else:
-            step_sharded_host(W + i)
+    else:
+        last_e2e = run_sharded(W, K, False)
+        assert np.array_equal(last_e2e[0], last[0]) and np.array_equal(last_e2e[1], last[1]), "host-query path != device-query path"
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -352,8 +362,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
-    avg_surv = (ix.stat("survivors") - surv0) / max(ix.stat("queries") - q0, 1)
-    d2h_bytes = int(ix.stat("fetch_bytes"))  # header + block table + first 1024 candidate slots, one cudaMemcpyAsync per query
+    avg_surv = (ix.stat("survivors") - surv0) / max(ix.stat("queries") - q0, 1) if world == 1 else None
+    # header + block table + first 1024 candidate slots per shard, one cudaMemcpyAsync per query (group)
+    d2h_bytes = int(ix.stat("fetch_bytes")) if world == 1 else int(exch.d2h_bytes_per_query)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -380,10 +391,13 @@ def main():
         "config": {"workload": workload, "metric": "L2", "k": k, "batch": 1, "rows": n, "dim": dim, "shards": world,
                    "l2_flush": "none needed: each step streams the whole shard (%.2f GB) which exceeds the 126 MB L2" % (shard_bytes / 1e9),
                    "result_mode": "exact reference slot replay (bit-exact rowids/order/distances vs distance-cpu.c)",
-                   "in_flight": 2},
+                   "in_flight": 2 if world == 1 else 2 * G,
+                   "exchange": None if world == 1 else f"groups of {G} independent queries: one NCCL all-gather of the shards' result blocks + one D2H per group, two groups in flight"},
         "e2e": {"value": K / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(pitch),
                 "d2h_bytes_per_step": d2h_bytes, "avg_candidates_per_query": avg_surv,
-                "note": "vsb_scan_topk: pinned query H2D + scan/filter kernels + one D2H copy of the candidate block (header + table + 1024 slots) + host slot replay"},
+                "note": ("vsb_scan_topk: pinned query H2D + scan/filter kernels + one D2H copy of the candidate block (header + table + 1024 slots) + host slot replay"
+                         if world == 1 else
+                         "vsb_scan_submit with HOST queries (pinned H2D per query) + scan/filter kernels on every rank + NCCL all-gather of the result blocks + D2H + host slot replay, same grouping as value")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "vsb::scan_kernel<int8,L2>", "avg_launch_ms": scan_ms, "launches_timed": prof["scan_launches"],

@@ -107,21 +107,46 @@ VSB_API int vsb_replay_topk(const vsb_candidate *cands, int n, int k, int *max_i
 /* ---- device-resident variants used by bench.py (inputs already in HBM) --------------------- */
 /* runs the scan kernels for ONE query that is already in device memory (pitch-padded, see
  * vsb_index_query_pitch) and leaves the candidates in the engine's output buffer; no host copies. */
-VSB_API int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k); /* returns the result slot (0/1) or <0 */
+VSB_API int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k); /* returns the result slot or <0 */
+/* general form: launches scan + filter for ONE query and returns immediately with the result slot (>= 0).  The query is
+ * either in device memory (query_on_device != 0, pitch-padded) or in HOST memory (dim elements; staged through the
+ * slot's pinned buffer with cudaMemcpyAsync, the xFilter argument of the reference, src/sqlite-vector.c:1774-1776).
+ * fetch != 0 also copies the slot's result block to pinned host memory for vsb_collect; pass 0 when the block is
+ * exchanged on the device (vsb_result_block + all-gather).  Up to vsb_index_stat("slots") queries may be in flight:
+ * slot < 0 hands slots out round-robin, slot >= 0 names the slot (a launcher that gathers groups of consecutive
+ * slots manages them itself); either way a slot must be collected/merged before it is used again. */
+VSB_API int vsb_scan_submit(vsb_index *ix, int metric, const void *query, int query_on_device, int k, int fetch, int slot);
 /* blocks until the engine stream is idle and converts the last device-side result into top-k. */
 VSB_API int vsb_collect_last(vsb_index *ix, int k, int64_t *out_rowids, double *out_dist, int *out_count);
-/* same for a given result slot: two launches may be in flight (slots alternate), so query i+1 can be scanning while
+/* same for a given result slot: several launches may be in flight (slots rotate), so query i+1 can be scanning while
  * the host finishes query i */
 VSB_API int vsb_collect(vsb_index *ix, int slot, int k, int64_t *out_rowids, double *out_dist, int *out_count);
 /* device address and size of a slot's result block (header + block table + first candidates) so that a launcher
- * can all-gather the shards' blocks on the device (NCCL) without a host round trip */
+ * can all-gather the shards' blocks on the device (NCCL) without a host round trip.  The blocks of all slots are
+ * contiguous (slot s at block(0) + s * bytes): one collective can move a group of consecutive slots. */
 VSB_API int vsb_result_block(vsb_index *ix, int slot, void **d_block, int64_t *bytes);
 /* host-side merge of `world` gathered result blocks (block r starts at blocks + r*block_stride) into the reference's
  * top-k; rows are numbered first_seq[r] + local and rowids are implicit (global row + 1).  Returns the row count. */
 VSB_API int vsb_merge_result_blocks(const void *blocks, int world, int64_t block_stride, const int64_t *first_seq, int k,
                                     int64_t *out_rowids, double *out_dist);
+/* ---- batched queries on a row-sharded column (BASELINE config 4: one shard per GPU) ----------------------------
+ * step 1, on every shard: the tensor-core batch path of vsb_scan_topk (same conditions: nq >= 16, f16/bf16/int8/uint8,
+ * not L1) over this shard, leaving in DEVICE memory one block with, per query, the rows that entered the shard-local
+ * slots in scan order (distance bits, local row).  *d_block / *bytes describe it (the same size on every shard for the
+ * same nq and k) so that a launcher can all-gather the blocks (NCCL).  Returns VSB_ERANGE when the batch path does not
+ * apply or a capacity was exceeded: use the per-query path (vsb_scan_candidates / vsb_scan_submit) then. */
+VSB_API int vsb_batch_shard_scan(vsb_index *ix, int metric, const void *queries, int nq, int k, void **d_block, int64_t *bytes);
+/* step 2, on any shard's GPU: `world` gathered blocks in shard (= scan) order, block r at d_blocks + r * block_stride in
+ * DEVICE memory of ix's GPU (complete before the call).  Replays them through the reference's slot algorithm
+ * (src/sqlite-vector.c:2145-2152, 2022-2069) on the GPU: exactly the result of one scan over the concatenated shards.
+ * out_seq[b*k + j] is the GLOBAL scan-order row index (first_seq[r] + local row) of result j of query b; map it to a
+ * rowid with vsb_index_lookup_rowids on the owning shard (implicit rowids: seq + 1). */
+VSB_API int vsb_batch_merge(vsb_index *ix, const void *d_blocks, int world, int64_t block_stride, const int64_t *first_seq, int nq,
+                            int k, int64_t *out_seq, double *out_dist, int *out_counts);
+/* out[i] = rowid of global row seq[i] when this shard owns it, else 0 (so shards can be summed) */
+VSB_API int vsb_index_lookup_rowids(const vsb_index *ix, const int64_t *seq, int64_t n, int64_t *out);
 VSB_API int vsb_index_query_pitch(const vsb_index *ix); /* bytes per query row on the device (multiple of 16) */
-/* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes","batches","batch_cands","batch_kept","tc_us","tc_rows","batch_us"}; -1 if unknown */
+/* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes","slots","batches","batch_cands","batch_kept","tc_us","tc_rows","batch_us"}; -1 if unknown */
 VSB_API int64_t vsb_index_stat(const vsb_index *ix, const char *name);
 VSB_API void *vsb_index_stream(vsb_index *ix);           /* cudaStream_t of the engine, for event timing */
 /* kernel launch counter (all kernels launched by this library since load) */
@@ -129,7 +154,7 @@ VSB_API int64_t vsb_kernel_launches(void);
 /* with option "time_kernels"=1 every launch is bracketed by CUDA events on the engine stream; this returns
  * (and resets) the summed device time and launch count of the scan kernel and of the filter kernel. */
 VSB_API int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double *filter_ms, int *filter_launches);
-/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat"}; returns previous value */
+/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat","epi2","batch_debug"}; returns previous value */
 VSB_API int vsb_set_option(const char *name, int value);
 
 #ifdef __cplusplus

@@ -43,10 +43,14 @@ _SIGNATURES = {
     "vsb_scan_candidates": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp]),
     "vsb_replay_topk": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "vsb_scan_device_query": (_i, [_vp, _i, _vp, _i]),
+    "vsb_scan_submit": (_i, [_vp, _i, _vp, _i, _i, _i, _i]),
     "vsb_collect_last": (_i, [_vp, _i, _vp, _vp, _vp]),
     "vsb_collect": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "vsb_result_block": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i64)]),
     "vsb_merge_result_blocks": (_i, [_vp, _i, _i64, _vp, _i, _vp, _vp]),
+    "vsb_batch_shard_scan": (_i, [_vp, _i, _vp, _i, _i, C.POINTER(_vp), C.POINTER(_i64)]),
+    "vsb_batch_merge": (_i, [_vp, _vp, _i, _i64, _vp, _i, _i, _vp, _vp, _vp]),
+    "vsb_index_lookup_rowids": (_i, [_vp, _vp, _i64, _vp]),
     "vsb_index_query_pitch": (_i, [_vp]),
     "vsb_index_stream": (_vp, [_vp]),
     "vsb_index_stat": (_i64, [_vp, C.c_char_p]),
@@ -201,11 +205,44 @@ class Index:
             self.eng.check(slot)
         return slot
 
+    def scan_submit(self, metric: int, query, k: int, on_device: bool = False, fetch: bool = True, slot: int = -1) -> int:
+        """asynchronous single-query scan; `query` is a device pointer (int) or a host array.  Returns the result slot."""
+        if on_device:
+            slot = self.eng.lib.vsb_scan_submit(self.h, metric, int(query), 1, k, int(fetch), slot)
+        else:
+            q = np.ascontiguousarray(query)
+            slot = self.eng.lib.vsb_scan_submit(self.h, metric, _ptr(q), 0, k, int(fetch), slot)
+        if slot < 0:
+            self.eng.check(slot)
+        return slot
+
     def result_block(self, slot: int):
         """(device pointer, bytes) of the slot's result block"""
         ptr, nbytes = _vp(), _i64()
         self.eng.check(self.eng.lib.vsb_result_block(self.h, slot, C.byref(ptr), C.byref(nbytes)))
         return int(ptr.value), int(nbytes.value)
+
+    def batch_shard_scan(self, metric: int, queries: np.ndarray, k: int):
+        """tensor-core batch path over this shard; returns (device pointer, bytes) of the shard's entry-log block"""
+        q2 = np.ascontiguousarray(queries).reshape(-1, queries.shape[-1])
+        ptr, nbytes = _vp(), _i64()
+        self.eng.check(self.eng.lib.vsb_batch_shard_scan(self.h, metric, _ptr(q2), q2.shape[0], k, C.byref(ptr), C.byref(nbytes)))
+        return int(ptr.value), int(nbytes.value)
+
+    def batch_merge(self, d_blocks: int, world: int, stride: int, first_seq, nq: int, k: int):
+        """replay `world` gathered entry-log blocks (device memory) on the GPU; returns (seq[nq,k], dist[nq,k], counts[nq])"""
+        seq = np.zeros((nq, k), dtype=np.int64)
+        dist = np.zeros((nq, k), dtype=np.float64)
+        counts = np.zeros(nq, dtype=np.int32)
+        fs = np.ascontiguousarray(first_seq, dtype=np.int64)
+        self.eng.check(self.eng.lib.vsb_batch_merge(self.h, d_blocks, world, stride, _ptr(fs), nq, k, _ptr(seq), _ptr(dist), _ptr(counts)))
+        return seq, dist, counts
+
+    def lookup_rowids(self, seq: np.ndarray) -> np.ndarray:
+        sq = np.ascontiguousarray(seq, dtype=np.int64)
+        out = np.zeros(sq.shape, dtype=np.int64)
+        self.eng.check(self.eng.lib.vsb_index_lookup_rowids(self.h, _ptr(sq), sq.size, _ptr(out)))
+        return out
 
     def collect(self, slot: int, k: int):
         ids = np.zeros(max(k, 1), dtype=np.int64)

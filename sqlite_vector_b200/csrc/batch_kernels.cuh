@@ -17,7 +17,10 @@
 namespace vsb {
 
 enum { TK_BF16 = 0, TK_F16 = 1, TK_I8 = 2, TK_U8 = 3 };
-constexpr int kTcThreads = 256;     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue
+// warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4.. : epilogue.  EPI = 1: warps 4-7 (one per TMEM lane quadrant)
+// drain all N accumulator columns; EPI = 2: warps 4-7 take columns [0, N/2), warps 8-11 columns [N/2, N) — two epilogue
+// warps per SM sub-partition, which is what small-K tiles need (the tile is drain-bound, not MMA-bound).
+__host__ __device__ constexpr int tc_threads(int epi) { return 128 + 128 * epi; }
 constexpr int kTcMaxStages = 8;
 constexpr int kTcM = 128;           // corpus rows per MMA tile
 constexpr int kTcKBytes = 128;      // one swizzle atom of K per stage
@@ -165,8 +168,9 @@ struct TileIter {
     }
 };
 
-template <int KIND, int MC, bool BSTAT>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmA,
+// CH: accumulator columns per epilogue step (64 = two 32-column TMEM loads in flight per buffer, 32 = one)
+template <int KIND, int MC, bool BSTAT, int EPI, int CH>
+__global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, const TcParams prm) {
     constexpr bool INT8 = (KIND == TK_I8 || KIND == TK_U8);
     extern __shared__ __align__(1024) uint8_t tsm[];
@@ -190,13 +194,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTcMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * EPI); }
         mbar_init(bfull, 1);
         mbar_init(bempty, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
-    for (int i = threadIdx.x; i < prm.NG * N; i += kTcThreads) qc_s[i] = __float_as_uint(prm.qc[i]);
+    for (int i = threadIdx.x; i < prm.NG * N; i += tc_threads(EPI)) qc_s[i] = __float_as_uint(prm.qc[i]);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -259,7 +263,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
             }
         }
     } else if (warp >= 4) {                                                    // ===== epilogue: TMEM -> registers -> threshold test
-        const int quad = warp & 3;
+        const int quad = warp & 3;                                             // TMEM lane quadrant this warp may read
+        const int c_lo = ((warp - 4) >> 2) * (N / EPI), c_hi = c_lo + N / EPI;  // accumulator columns of this warp
         for (long long tl = 0; tl < ti.count; ++tl) {
             long long mt; int ng;
             ti.at(tl, mt, ng);
@@ -286,10 +291,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
             const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * N);
             auto issue = [&](int cb, uint32_t *v) {
                 tmem_ld32_nowait(tbase + (uint32_t)cb, v);
-                if (cb + 32 < N) tmem_ld32_nowait(tbase + (uint32_t)cb + 32, v + 32);
+                if constexpr (CH == 64) {
+                    if (cb + 32 < c_hi) tmem_ld32_nowait(tbase + (uint32_t)cb + 32, v + 32);
+                }
             };
             auto process = [&](int cb, const uint32_t *v) {
-                const bool two = (cb + 32) < N;
+                const bool two = (CH == 64) && (cb + 32) < c_hi;
                 const uint4 *qc4 = reinterpret_cast<const uint4 *>(qc_s + ng * N + cb);
                 bool any0 = false, any1 = false;
 #pragma unroll
@@ -298,12 +305,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
                     any0 |= tc_hit<INT8, MC>(v[4 * j4 + 0], c.x, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 1], c.y, rowf, rowi) |
                             tc_hit<INT8, MC>(v[4 * j4 + 2], c.z, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 3], c.w, rowf, rowi);
                 }
-                if (two) {
+                if constexpr (CH == 64) {
+                    if (two) {
 #pragma unroll
-                    for (int j4 = 8; j4 < 16; ++j4) {
-                        const uint4 c = qc4[j4];
-                        any1 |= tc_hit<INT8, MC>(v[4 * j4 + 0], c.x, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 1], c.y, rowf, rowi) |
-                                tc_hit<INT8, MC>(v[4 * j4 + 2], c.z, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 3], c.w, rowf, rowi);
+                        for (int j4 = 8; j4 < 16; ++j4) {
+                            const uint4 c = qc4[j4];
+                            any1 |= tc_hit<INT8, MC>(v[4 * j4 + 0], c.x, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 1], c.y, rowf, rowi) |
+                                    tc_hit<INT8, MC>(v[4 * j4 + 2], c.z, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 3], c.w, rowf, rowi);
+                        }
                     }
                 }
                 const bool any = (any0 | any1) && rowvalid;
@@ -313,9 +322,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
                     if (any) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) mask0 |= (tc_hit<INT8, MC>(v[j], qc[j], rowf, rowi) ? 1u : 0u) << j;
-                        if (two) {
+                        if constexpr (CH == 64) {
+                            if (two) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) mask1 |= (tc_hit<INT8, MC>(v[32 + j], qc[32 + j], rowf, rowi) ? 1u : 0u) << j;
+                                for (int j = 0; j < 32; ++j) mask1 |= (tc_hit<INT8, MC>(v[32 + j], qc[32 + j], rowf, rowi) ? 1u : 0u) << j;
+                            }
                         }
                         const int ncol = prm.nq - (ng * N + cb);                // padded query columns are never reported
                         mask0 &= (ncol >= 32) ? 0xFFFFFFFFu : (ncol <= 0 ? 0u : ((1u << ncol) - 1u));
@@ -346,16 +357,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
                     }
                 }
             };
-            uint32_t va[64], vb[64];
-            issue(0, va);
-            for (int cb = 0; cb < N; cb += 128) {
+            uint32_t va[CH], vb[CH];
+            issue(c_lo, va);
+            for (int cb = c_lo; cb < c_hi; cb += 2 * CH) {
                 tmem_wait_ld();
-                if (cb + 64 < N) issue(cb + 64, vb);
+                if (cb + CH < c_hi) issue(cb + CH, vb);
                 process(cb, va);
-                if (cb + 64 < N) {
+                if (cb + CH < c_hi) {
                     tmem_wait_ld();
-                    if (cb + 128 < N) issue(cb + 128, va);
-                    process(cb + 64, vb);
+                    if (cb + 2 * CH < c_hi) issue(cb + 2 * CH, va);
+                    process(cb + CH, vb);
                 }
             }
             tc_fence_before();
@@ -533,7 +544,45 @@ struct ReplayParams {
     const void *qnorm;      // [nq] float / int sum of squares of each query
     float rnmax;            // max row norm (fp kinds, DOT slack)
     int level0;             // 1: initialise the slots first
+    // optional (row-sharded batches): log of the rows that entered the slots, in scan order.  A row that does not
+    // enter the slots of its own shard scanned alone cannot enter them in the full scan either (the bound there is
+    // tighter), so the concatenation of the shards' logs replayed in shard order reproduces the full scan exactly.
+    uint2 *acc_log;         // [nq][acc_cap] (dist bits, local row) or nullptr
+    int *acc_count;         // [nq] entries logged so far (may exceed acc_cap => overflow, detected by the merge)
+    int acc_cap;
 };
+
+// The reference's slot update for up to 32 (distance, row) offers held one per lane, in lane order:
+// strict '<' against the slot at max_index (src/sqlite-vector.c:2145), then vFullScanFindMaxIndex (:2022-2049, first
+// index of the maximum).  sd/sr: this query's slots (kcap entries, entries >= k hold -INF); on_accept(dist, row) is
+// called by the whole warp for every offer that enters.
+template <class F>
+__device__ __forceinline__ void warp_offer32(float *sd, unsigned *sr, int kcap, int lane, float d, unsigned row, int &mi, float &cur,
+                                             F on_accept) {
+    unsigned m = __ballot_sync(0xFFFFFFFFu, d < cur);
+    while (m) {
+        const int sl = __ffs(m) - 1;
+        m &= m - 1;
+        const float dv = __shfl_sync(0xFFFFFFFFu, d, sl);
+        const unsigned rv = __shfl_sync(0xFFFFFFFFu, row, sl);
+        if (dv < cur) {
+            if (lane == 0) { sd[mi] = dv; sr[mi] = rv; }
+            __syncwarp();
+            float best = -INFINITY;
+            int bi = 0x7FFFFFFF;
+            for (int j = lane; j < kcap; j += 32) {
+                const float v = sd[j];
+                if (v > best) { best = v; bi = j; }
+            }
+            const uint32_t key = fkey(best);
+            const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, key);
+            const int cand = (key == mx) ? bi : 0x7FFFFFFF;
+            mi = __reduce_min_sync(0xFFFFFFFFu, cand);
+            cur = funkey(mx);
+            on_accept(dv, rv);
+        }
+    }
+}
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
@@ -592,38 +641,71 @@ __global__ void replay_kernel(const ReplayParams rp) {
     const unsigned seg1 = a;
     int mi = rp.slot_mi[q];
     float cur = sd[mi];
+    int acc_n = (rp.acc_log != nullptr && !rp.level0) ? rp.acc_count[q] : 0;
+    uint2 *alog = rp.acc_log ? rp.acc_log + (size_t)q * rp.acc_cap : nullptr;
     for (unsigned base = seg0; base < seg1; base += 32) {
         const unsigned i = base + lane;
         const float d = (i < seg1) ? rp.val[i] : INFINITY;
         const unsigned row = (i < seg1) ? (unsigned)(rp.key[i] & 0xFFFFFFFFu) : 0u;
-        unsigned m = __ballot_sync(0xFFFFFFFFu, d < cur);
-        while (m) {
-            const int sl = __ffs(m) - 1;
-            m &= m - 1;
-            const float dv = __shfl_sync(0xFFFFFFFFu, d, sl);
-            const unsigned rv = __shfl_sync(0xFFFFFFFFu, row, sl);
-            if (dv < cur) {                                   // strict, src/sqlite-vector.c:2145
-                if (lane == 0) { sd[mi] = dv; sr[mi] = rv; }
-                __syncwarp();
-                // first index holding the maximum (vFullScanFindMaxIndex, :2022-2049)
-                float best = -INFINITY;
-                int bi = 0x7FFFFFFF;
-                for (int j = lane; j < rp.kcap; j += 32) {
-                    const float v = sd[j];
-                    if (v > best) { best = v; bi = j; }
-                }
-                const uint32_t key = fkey(best);
-                const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, key);
-                const int cand = (key == mx) ? bi : 0x7FFFFFFF;
-                mi = __reduce_min_sync(0xFFFFFFFFu, cand);
-                cur = funkey(mx);
-            }
-        }
+        warp_offer32(sd, sr, rp.kcap, lane, d, row, mi, cur, [&](float dv, unsigned rv) {
+            if (alog != nullptr && lane == 0 && acc_n < rp.acc_cap) alog[acc_n] = make_uint2(__float_as_uint(dv), rv);
+            ++acc_n;
+        });
     }
     if (lane == 0) {
         rp.slot_mi[q] = mi;
         rp.U[q] = cur;
         rp.qc[q] = conservative_qc(rp.kind, rp.mc, rp.root, cur, rp.qnorm, q, rp.rnmax);
+        if (rp.acc_log != nullptr) rp.acc_count[q] = acc_n;
+    }
+}
+
+// ------------------------------------------------------------------ row-sharded batches: merge of the shards' entry logs
+// block of one shard: [hdr 64 B: nq, k, acc_cap, 0...][counts: int x round_up(nq,16)][log: nq x acc_cap x uint2]
+__host__ __device__ inline size_t acc_block_counts_off() { return 64; }
+__host__ __device__ inline size_t acc_block_log_off(int nq) { return 64 + 4 * (size_t)((nq + 15) & ~15); }
+__host__ __device__ inline size_t acc_block_bytes(int nq, int acc_cap) { return acc_block_log_off(nq) + 8 * (size_t)nq * acc_cap; }
+
+struct MergeParams {
+    const uint8_t *blocks;      // world blocks, block r at blocks + r * block_stride (device memory)
+    long long block_stride;
+    int world, nq, k, kcap, acc_cap;
+    const long long *first_seq; // [world] global scan-order index of each shard's first row (device)
+    float *slot_d;              // [nq][kcap] out
+    unsigned *slot_row;         // [nq][kcap] out: GLOBAL row index
+    int *status;                // [0] |= 1 when a shard's log overflowed, |= 2 on a malformed block
+};
+
+// one warp per query: the shards' logs, in shard (= scan) order, through the reference's slot update
+__global__ void merge_logs_kernel(const MergeParams mp) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= mp.nq) return;
+    float *sd = mp.slot_d + (size_t)q * mp.kcap;
+    unsigned *sr = mp.slot_row + (size_t)q * mp.kcap;
+    for (int j = lane; j < mp.kcap; j += 32) { sd[j] = (j < mp.k) ? INFINITY : -INFINITY; sr[j] = 0; }
+    __syncwarp();
+    int mi = 0;
+    float cur = INFINITY;
+    for (int r = 0; r < mp.world; ++r) {
+        const uint8_t *blk = mp.blocks + (size_t)r * (size_t)mp.block_stride;
+        const int *hdr = reinterpret_cast<const int *>(blk);
+        if (hdr[0] != mp.nq || hdr[1] != mp.k || hdr[2] != mp.acc_cap) {
+            if (lane == 0) atomicOr(mp.status, 2);
+            return;
+        }
+        const int cnt = reinterpret_cast<const int *>(blk + acc_block_counts_off())[q];
+        if (cnt > mp.acc_cap) {
+            if (lane == 0) atomicOr(mp.status, 1);
+            return;
+        }
+        const uint2 *lg = reinterpret_cast<const uint2 *>(blk + acc_block_log_off(mp.nq)) + (size_t)q * mp.acc_cap;
+        const unsigned base_row = (unsigned)mp.first_seq[r];
+        for (int base = 0; base < cnt; base += 32) {
+            const int i = base + lane;
+            const uint2 e = (i < cnt) ? lg[i] : make_uint2(0x7F800000u, 0u);
+            warp_offer32(sd, sr, mp.kcap, lane, __uint_as_float(e.x), base_row + e.y, mi, cur, [](float, unsigned) {});
+        }
     }
 }
 

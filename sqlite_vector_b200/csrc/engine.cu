@@ -37,6 +37,7 @@ int g_opt_ring_bytes = 0;      // 0: use all shared memory left
 int g_opt_no_batch = 0;        // 1: never take the tensor-core batch path
 int g_opt_batch_debug = 0;     // 1: print per-stage timings of the batch path to stderr (serialises the stages)
 int g_opt_bstat = 0;           // 1: park the query group in shared memory when it fits (measured: no gain, off by default)
+int g_opt_epi2 = 1;            // 1: tc_scan_kernel drains the accumulators with 8 epilogue warps (two per TMEM lane quadrant)
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
 
 int fail(int code, const char *fmt, ...) {
@@ -69,19 +70,23 @@ int elem_size(int vtype) {
 constexpr size_t kStageBuf = 32u << 20;  // pinned staging buffers for preload (two of them)
 constexpr int kOutCap = 1 << 16;         // survivor capacity per query (mapped pinned)
 constexpr int kMaxK = 256;               // candidate path; larger k uses the all-distances path
-constexpr int kSlots = 2;                // result slots (pipelining of batches)
+constexpr int kSlots = 16;               // result slots: queries in flight (the sharded exchange gathers groups of them)
 
 // result block of one query, written by filter_kernel into DEVICE memory and fetched with one async copy:
-//   [hdr: 16 ints][table: kTableCap x int2][survivors: kOutCap x uint2]; the first kFirstFetch survivors travel
-//   with the header, the (rare) rest in a second copy.  (Zero-copy writes of ~300 scattered 8-byte records over
-//   PCIe made the filter kernel 5x slower than writing to HBM and copying once.)
+//   head = [hdr: 16 ints][table: kTableCap x int2][first kFirstFetch survivors x uint2]   (kHeadBytes, what travels)
+//   tail = the (rare) survivors beyond kFirstFetch, fetched by a second copy.
+// The heads of all slots are ONE contiguous allocation (slot s at s * kHeadBytes), so a launcher can all-gather the
+// heads of a group of consecutive slots with a single collective.  (Zero-copy writes of ~300 scattered 8-byte records
+// over PCIe made the filter kernel 5x slower than writing to HBM and copying once.)
 constexpr int kTableCap = 512;
 constexpr int kFirstFetch = 1024;
 constexpr size_t kResHdrBytes = 64 + sizeof(int2) * kTableCap;
+constexpr size_t kHeadBytes = kResHdrBytes + sizeof(uint2) * kFirstFetch;
 
 struct Slot {
-    uint8_t *d_res = nullptr, *h_res = nullptr;
-    uint2 *h_out = nullptr, *d_out = nullptr;
+    uint8_t *d_res = nullptr, *h_res = nullptr;      // this slot's head inside vsb_index::d_heads / h_heads
+    uint2 *h_out = nullptr, *d_out = nullptr;        // first kFirstFetch survivors (inside the head)
+    uint2 *h_tail = nullptr, *d_tail = nullptr;      // survivors kFirstFetch.. (own allocations)
     int2 *h_table = nullptr, *d_table = nullptr;
     int *h_hdr = nullptr, *d_hdr = nullptr;
     uint8_t *h_query = nullptr, *d_query = nullptr;  // pinned staging + device copy of the query
@@ -110,6 +115,7 @@ struct vsb_index {
     uint2 *d_logs = nullptr;
     int *d_counts = nullptr;
     Slot slot[kSlots];
+    uint8_t *d_heads = nullptr, *h_heads = nullptr;   // kSlots x kHeadBytes
     bool slots_ready = false;
     float *d_dist_all = nullptr;
     int last_slot = -1, last_metric = 0;
@@ -194,13 +200,17 @@ Plan make_plan(const vsb_index *ix, int kcap) {
 
 int ensure_slots(vsb_index *ix) {
     if (ix->slots_ready) return VSB_OK;
+    CU(cudaMalloc((void **)&ix->d_heads, kHeadBytes * kSlots));
+    CU(cudaMemset(ix->d_heads, 0, kHeadBytes * kSlots));
+    CU(cudaHostAlloc((void **)&ix->h_heads, kHeadBytes * kSlots, cudaHostAllocDefault));
+    memset(ix->h_heads, 0, kHeadBytes * kSlots);
     for (int i = 0; i < kSlots; ++i) {
         Slot &s = ix->slot[i];
-        const size_t res_bytes = kResHdrBytes + sizeof(uint2) * kOutCap;
-        CU(cudaMalloc((void **)&s.d_res, res_bytes));
-        CU(cudaMemset(s.d_res, 0, kResHdrBytes));
-        CU(cudaHostAlloc((void **)&s.h_res, res_bytes, cudaHostAllocDefault));
-        memset(s.h_res, 0, kResHdrBytes);
+        s.d_res = ix->d_heads + kHeadBytes * i;
+        s.h_res = ix->h_heads + kHeadBytes * i;
+        const size_t tail_bytes = sizeof(uint2) * (size_t)(kOutCap - kFirstFetch);
+        CU(cudaMalloc((void **)&s.d_tail, tail_bytes));
+        CU(cudaHostAlloc((void **)&s.h_tail, tail_bytes, cudaHostAllocDefault));
         s.d_hdr = (int *)s.d_res; s.h_hdr = (int *)s.h_res;
         s.d_table = (int2 *)(s.d_res + 64); s.h_table = (int2 *)(s.h_res + 64);
         s.d_out = (uint2 *)(s.d_res + kResHdrBytes); s.h_out = (uint2 *)(s.h_res + kResHdrBytes);
@@ -232,7 +242,8 @@ int ensure_workspace(vsb_index *ix, int k) {
 }
 
 // launches scan (+ filter when k > 0) for the query in `d_query` (pitch bytes) on ix->stream
-int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *slot, float *d_dist_all) {
+// fetch: copy the slot's head to pinned host memory afterwards (false when the head is all-gathered on the device)
+int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *slot, float *d_dist_all, bool fetch = true) {
     int root = 0;
     const int mc = metric_class(metric, &root);
     if (mc < 0) return fail(VSB_EINVAL, "unknown distance metric %d", metric);
@@ -288,6 +299,8 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         f.counts = ix->d_counts;
         f.logcap = ix->ws_logcap;
         f.out = slot->d_out;
+        f.headcap = kFirstFetch;
+        f.out_tail = slot->d_tail;
         f.outcap = kOutCap;
         f.table = slot->d_table;
         f.hdr = slot->d_hdr;
@@ -309,7 +322,7 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         ++g_launches;
         if (pev) CU(cudaEventRecord(pev[2], ix->stream));
         if (nblocks > kTableCap) return fail(VSB_ERANGE, "too many filter blocks (%d)", nblocks);
-        CU(cudaMemcpyAsync(slot->h_res, slot->d_res, kResHdrBytes + sizeof(uint2) * kFirstFetch, cudaMemcpyDeviceToHost, ix->stream));
+        if (fetch) CU(cudaMemcpyAsync(slot->h_res, slot->d_res, kHeadBytes, cudaMemcpyDeviceToHost, ix->stream));
         CU(cudaEventRecord(slot->done, ix->stream));
     }
     return VSB_OK;
@@ -361,7 +374,7 @@ int gather_survivors(vsb_index *ix, Slot *slot, std::vector<uint2> &out, bool *o
     if (slot->h_hdr[1]) { *overflow = true; return 0; }
     const int total = slot->h_hdr[0];
     if (total > kFirstFetch) {  // rare: fetch the tail of the survivor list
-        if (cudaMemcpyAsync(slot->h_out + kFirstFetch, slot->d_out + kFirstFetch, sizeof(uint2) * (size_t)(total - kFirstFetch),
+        if (cudaMemcpyAsync(slot->h_tail, slot->d_tail, sizeof(uint2) * (size_t)(total - kFirstFetch),
                             cudaMemcpyDeviceToHost, ix->stream) != cudaSuccess ||
             cudaStreamSynchronize(ix->stream) != cudaSuccess)
             return fail(VSB_ECUDA, "fetching %d survivors failed: %s", total, cudaGetErrorString(cudaGetLastError()));
@@ -370,7 +383,10 @@ int gather_survivors(vsb_index *ix, Slot *slot, std::vector<uint2> &out, bool *o
     out.reserve((size_t)total);
     for (int b = 0; b < slot->nblocks; ++b) {
         const int2 t = slot->h_table[b];
-        for (int i = 0; i < t.y; ++i) out.push_back(slot->h_out[t.x + i]);
+        for (int i = 0; i < t.y; ++i) {
+            const int at = t.x + i;
+            out.push_back(at < kFirstFetch ? slot->h_out[at] : slot->h_tail[at - kFirstFetch]);
+        }
     }
     ix->st_queries++;
     ix->st_survivors += (long long)out.size();
@@ -476,6 +492,7 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "time_kernels")) p = &g_opt_time_kernels;
     else if (!strcmp(name, "no_batch")) p = &g_opt_no_batch;
     else if (!strcmp(name, "bstat")) p = &g_opt_bstat;
+    else if (!strcmp(name, "epi2")) p = &g_opt_epi2;
     else if (!strcmp(name, "batch_debug")) p = &g_opt_batch_debug;
     if (!p) return fail(VSB_EINVAL, "unknown option %s", name);
     int old = *p;
@@ -642,7 +659,8 @@ int64_t vsb_index_stat(const vsb_index *ix, const char *name) {
     if (!strcmp(name, "tc_us")) return ix->st_tc_us;
     if (!strcmp(name, "batch_us")) return ix->st_batch_us;
     if (!strcmp(name, "tc_rows")) return ix->st_tc_rows;
-    if (!strcmp(name, "fetch_bytes")) return (long long)(kResHdrBytes + sizeof(uint2) * kFirstFetch);
+    if (!strcmp(name, "fetch_bytes")) return (long long)kHeadBytes;
+    if (!strcmp(name, "slots")) return kSlots;
     if (!strcmp(name, "filter_blocks")) return (ix->num_sms * kWarps + kFilterWarps - 1) / kFilterWarps;
     return -1;
 }
@@ -658,13 +676,15 @@ void vsb_index_free(vsb_index *ix) {
     }
     for (int i = 0; i < kSlots; ++i) {
         Slot &s = ix->slot[i];
-        if (s.h_res) cudaFreeHost(s.h_res);
-        if (s.d_res) cudaFree(s.d_res);
+        if (s.h_tail) cudaFreeHost(s.h_tail);
+        if (s.d_tail) cudaFree(s.d_tail);
         if (s.h_query) cudaFreeHost(s.h_query);
         if (s.d_query) cudaFree(s.d_query);
         if (s.d_ctrl) cudaFree(s.d_ctrl);
         if (s.done) cudaEventDestroy(s.done);
     }
+    if (ix->h_heads) cudaFreeHost(ix->h_heads);
+    if (ix->d_heads) cudaFree(ix->d_heads);
     if (ix->d_lists) cudaFree(ix->d_lists);
     if (ix->d_logs) cudaFree(ix->d_logs);
     if (ix->d_counts) cudaFree(ix->d_counts);
@@ -793,27 +813,44 @@ int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double 
     return VSB_OK;
 }
 
-int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k) {
+int vsb_scan_submit(vsb_index *ix, int metric, const void *query, int query_on_device, int k, int fetch, int want_slot) {
     if (check_index(ix)) return VSB_EINVAL;
-    if (!d_query || k <= 0 || k > kMaxK) return fail(VSB_EINVAL, "bad device scan arguments (k must be 1..%d)", kMaxK);
+    if (!query || k <= 0 || k > kMaxK) return fail(VSB_EINVAL, "bad scan arguments (k must be 1..%d)", kMaxK);
     CU(cudaSetDevice(ix->device));
     int rc = ensure_slots(ix);
     if (rc) return rc;
     rc = ensure_workspace(ix, k);
     if (rc) return rc;
-    const int si = (ix->last_slot + 1) % kSlots;
-    rc = launch_scan(ix, metric, (const uint8_t *)d_query, k, &ix->slot[si], nullptr);
+    if (want_slot >= kSlots) return fail(VSB_EINVAL, "slot %d out of range (have %d)", want_slot, kSlots);
+    const int si = want_slot >= 0 ? want_slot : (ix->last_slot + 1) % kSlots;
+    Slot *slot = &ix->slot[si];
+    const uint8_t *dq = (const uint8_t *)query;
+    if (!query_on_device) {
+        // the slot's pinned staging buffer is free once the slot's previous query has completed on the device
+        if (slot->seq > 0) CU(cudaEventSynchronize(slot->done));
+        rc = stage_query(ix, slot, query);
+        if (rc) return rc;
+        dq = slot->d_query;
+    }
+    rc = launch_scan(ix, metric, dq, k, slot, nullptr, fetch != 0);
     if (rc) return rc;
     ix->last_slot = si;
     ix->last_metric = metric;
-    return si;   // slot id (>= 0) for vsb_collect
+    return si;   // slot id (>= 0) for vsb_collect / vsb_result_block
+}
+
+int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k) {
+    return vsb_scan_submit(ix, metric, d_query, 1, k, 1, -1);
 }
 
 int vsb_result_block(vsb_index *ix, int slot_id, void **d_block, int64_t *bytes) {
     if (check_index(ix)) return VSB_EINVAL;
-    if (slot_id < 0 || slot_id >= kSlots || !ix->slots_ready) return fail(VSB_EINVAL, "bad slot");
+    if (slot_id < 0 || slot_id >= kSlots) return fail(VSB_EINVAL, "bad slot");
+    CU(cudaSetDevice(ix->device));
+    int rc = ensure_slots(ix);
+    if (rc) return rc;
     if (d_block) *d_block = ix->slot[slot_id].d_res;
-    if (bytes) *bytes = (int64_t)(kResHdrBytes + sizeof(uint2) * kFirstFetch);
+    if (bytes) *bytes = (int64_t)kHeadBytes;
     return VSB_OK;
 }
 
@@ -841,6 +878,44 @@ int vsb_merge_result_blocks(const void *blocks, int world, int64_t block_stride,
         }
     }
     return slots_finish(s);
+}
+
+int vsb_batch_shard_scan(vsb_index *ix, int metric, const void *queries, int nq, int k, void **d_block, int64_t *bytes) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (!queries || nq <= 0 || k <= 0 || !d_block || !bytes) return fail(VSB_EINVAL, "bad batch scan arguments");
+    if (!batch_supported(ix, metric, nq, k))
+        return fail(VSB_ERANGE, "no tensor-core batch path for this shard (type %d, metric %d, %d queries, k %d, %lld rows)", ix->vtype, metric,
+                    nq, k, ix->n);
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = batch_levels(ix, metric, queries, nq, k, true);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ix->stream));
+    ix->st_batch_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    BatchWs *w = (BatchWs *)ix->batch;
+    *d_block = w->d_acc;
+    *bytes = (int64_t)acc_block_bytes(nq, acc_cap_of(k));
+    return VSB_OK;
+}
+
+int vsb_batch_merge(vsb_index *ix, const void *d_blocks, int world, int64_t block_stride, const int64_t *first_seq, int nq, int k,
+                    int64_t *out_seq, double *out_dist, int *out_counts) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (!d_blocks || world <= 0 || !first_seq || nq <= 0 || k <= 0 || k > kMaxK || !out_seq || !out_dist)
+        return fail(VSB_EINVAL, "bad batch merge arguments");
+    if (block_stride < (int64_t)acc_block_bytes(nq, acc_cap_of(k))) return fail(VSB_EINVAL, "block stride smaller than a block");
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = batch_merge(ix, d_blocks, world, block_stride, first_seq, nq, k, out_seq, out_dist, out_counts);
+    ix->st_batch_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+int vsb_index_lookup_rowids(const vsb_index *ix, const int64_t *seq, int64_t n, int64_t *out) {
+    if (!ix || (!seq && n > 0) || (!out && n > 0) || n < 0) return fail(VSB_EINVAL, "bad lookup arguments");
+    for (int64_t i = 0; i < n; ++i) {
+        const long long local = (long long)seq[i] - ix->first_seq;
+        out[i] = (local >= 0 && local < ix->n) ? rowid_of(ix, (uint32_t)local) : 0;
+    }
+    return VSB_OK;
 }
 
 int vsb_collect_last(vsb_index *ix, int k, int64_t *out_rowids, double *out_dist, int *out_count) {

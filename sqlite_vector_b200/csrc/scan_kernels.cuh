@@ -468,8 +468,10 @@ struct FilterParams {
     const uint2 *logs;  // [S][logcap]
     const int *counts;  // [S]
     int logcap;
-    uint2 *out;         // survivors (dist bits, local row), grouped by block in stream order
-    int outcap;
+    uint2 *out;         // survivors (dist bits, local row), grouped by block in stream order: the first headcap of them
+    int headcap;        //   go to out (inside the slot's head, the part that travels), the rest to out_tail
+    uint2 *out_tail;
+    int outcap;         // total capacity (head + tail)
     int2 *table;        // [gridDim.x] (base, count) of each block's survivors in out
     int *hdr;           // hdr[0] = total survivors, hdr[1] = overflow flag, hdr[2] = sequence number
     int *ctrl;          // device: [0] cursor, [1] overflow from scan_kernel, [2] blocks done
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
         const bool keep = __uint_as_float(ereg[i].x) < T;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
         const int off = wr + __popc(m & ((1u << lane) - 1u));
-        if (keep && off < fp.outcap) fp.out[off] = ereg[i];
+        if (keep && off < fp.outcap) *(off < fp.headcap ? fp.out + off : fp.out_tail + (off - fp.headcap)) = ereg[i];
         wr += __popc(m);
     }
     for (int base = kLogRegs * 32; base < n_log; base += 32) {
@@ -683,7 +685,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
         if (j < n_log) { e = lg[j]; keep = __uint_as_float(e.x) < T; }
         const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
         const int off = wr + __popc(m & ((1u << lane) - 1u));
-        if (keep && off < fp.outcap) fp.out[off] = e;
+        if (keep && off < fp.outcap) *(off < fp.headcap ? fp.out + off : fp.out_tail + (off - fp.headcap)) = e;
         wr += __popc(m);
     }
     // last block publishes the header and re-arms the control words for the next query.  The host only reads the

@@ -71,50 +71,106 @@ class _DevView:
 
 
 class DeviceExchange:
-    """Fast path of the sharded scan: every rank launches its scan + filter on the engine stream, the fixed-size result
-    blocks are all-gathered device-to-device (NCCL over NVLink) and one D2H copy hands them to vsb_merge_result_blocks.
+    """Fast path of the sharded scan.  Every rank launches scan + filter of a GROUP of queries on the engine stream
+    (one result slot each; the slots' result blocks are contiguous in device memory), the group's blocks are
+    all-gathered device-to-device with ONE collective (NCCL over NVLink), one D2H copy brings them to pinned host
+    memory and vsb_merge_result_blocks replays the reference's slot algorithm per query.  Groups are pipelined: while
+    the blocks of group g are exchanged and merged, the GPU is already scanning group g+1.
     Requires implicit rowids (rowid = global row + 1), which is what the preloaded benchmark shards use."""
 
-    def __init__(self, ix, engine, world: int, bounds, device):
+    def __init__(self, ix, engine, world: int, bounds, device, group: int = 4):
         import torch
         self.torch, self.ix, self.eng, self.world = torch, ix, engine, world
         self.first_seq = np.asarray(bounds[:world], dtype=np.int64)
-        self.views = []
-        for slot in (0, 1):
-            ptr, nbytes = None, None
-            self.views.append(None)
         self.device = device
         self.estream = torch.cuda.ExternalStream(ix.stream, device=device)
-        self.gathered = None
-        self.host = None
+        nslots = ix.stat("slots")
+        self.group = max(1, min(group, nslots // 2))
+        self.ngroups = nslots // self.group          # slot groups used round-robin; >= 2 so that two can be in flight
+        base, nbytes = ix.result_block(0)
+        self.stride = nbytes
+        self.heads = torch.as_tensor(_DevView(base, nslots * nbytes), device=device)
+        gbytes = world * self.group * nbytes
+        self.gathered = [torch.empty(gbytes, dtype=torch.uint8, device=device) for _ in range(self.ngroups)]
+        self.host = [torch.empty(gbytes, dtype=torch.uint8).pin_memory() for _ in range(self.ngroups)]
+        self.next_group = 0
 
-    def _view(self, slot):
-        if self.views[slot] is None:
-            ptr, nbytes = self.ix.result_block(slot)
-            self.views[slot] = self.torch.as_tensor(_DevView(ptr, nbytes), device=self.device)
-            if self.gathered is None:
-                self.gathered = self.torch.empty(self.world * nbytes, dtype=self.torch.uint8, device=self.device)
-                self.host = self.torch.empty(self.world * nbytes, dtype=self.torch.uint8).pin_memory()
-                self.stride = nbytes
-        return self.views[slot]
-
-    def submit(self, metric: int, d_query_ptr: int, k: int):
-        """launch scan + filter of one query on the engine stream; returns a ticket for finish()"""
-        slot = self.ix.scan_device_query(metric, d_query_ptr, k)
-        return slot, self.estream.record_event(), k
+    def submit(self, metric: int, queries, k: int, on_device: bool = True):
+        """launch scan + filter for up to `group` queries (device pointers, or host arrays when on_device is False);
+        returns a ticket for finish()"""
+        nq = len(queries)
+        if not 0 < nq <= self.group:
+            raise ValueError(f"a group holds 1..{self.group} queries")
+        gi = self.next_group
+        self.next_group = (gi + 1) % self.ngroups
+        for j, q in enumerate(queries):
+            self.ix.scan_submit(metric, q, k, on_device=on_device, fetch=False, slot=gi * self.group + j)
+        return gi, nq, self.estream.record_event(), k
 
     def finish(self, ticket):
-        """all-gather the shards' result blocks of a submitted query and merge them (same result on every rank)"""
+        """all-gather the shards' result blocks of a submitted group and merge them; returns one (rowids, distances)
+        pair per query, the same on every rank"""
         import torch.distributed as dist
         torch = self.torch
-        slot, ev, k = ticket
-        blk = self._view(slot)
+        gi, nq, ev, k = ticket
+        lo = gi * self.group * self.stride
+        blk = self.heads[lo:lo + nq * self.stride]
+        out = self.gathered[gi][:self.world * nq * self.stride]
+        host = self.host[gi][:self.world * nq * self.stride]
         cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(ev)                                 # only this query; a later submit may still be scanning
-        dist.all_gather_into_tensor(self.gathered, blk)
-        self.host.copy_(self.gathered, non_blocking=True)
+        cur.wait_event(ev)                                 # only this group; a later group may still be scanning
+        dist.all_gather_into_tensor(out, blk)              # rank r's blocks land at r * nq * stride
+        host.copy_(out, non_blocking=True)
         cur.synchronize()
-        return self.eng.merge_result_blocks(self.host.numpy(), self.world, self.stride, self.first_seq, k)
+        hn = host.numpy()
+        return [self.eng.merge_result_blocks(hn[j * self.stride:], self.world, nq * self.stride, self.first_seq, k)
+                for j in range(nq)]
 
-    def query(self, metric: int, d_query_ptr: int, k: int):
-        return self.finish(self.submit(metric, d_query_ptr, k))
+    def query(self, metric: int, query, k: int, on_device: bool = True):
+        return self.finish(self.submit(metric, [query], k, on_device))[0]
+
+    @property
+    def d2h_bytes_per_query(self) -> int:
+        return self.world * self.stride
+
+
+def sharded_batch_topk(ix, metric: int, queries: np.ndarray, k: int, bounds, device, implicit_rowids: bool = True):
+    """Batched queries over a row-sharded column (BASELINE config 4).  Every rank runs the tensor-core batch path over
+    its shard (vsb_batch_shard_scan), the shards' entry-log blocks are all-gathered device-to-device (NCCL over NVLink)
+    and every rank replays them in shard order on its GPU (vsb_batch_merge) — bit for bit the result of one scan over the
+    whole column.  Returns one (rowids, distances) pair per query, or None on every rank when the batch path does not
+    apply to some shard (the caller then uses the per-query exchange)."""
+    import torch
+    import torch.distributed as dist
+
+    from .api import VsbError
+
+    world = dist.get_world_size()
+    q2 = np.ascontiguousarray(queries).reshape(-1, queries.shape[-1])
+    nq = q2.shape[0]
+    ptr = nbytes = 0
+    try:
+        ptr, nbytes = ix.batch_shard_scan(metric, q2, k)
+        bad = 0
+    except VsbError:
+        bad = 1
+    # a shard that cannot take the batch path must not leave the others waiting in the collective
+    flag = torch.tensor([bad], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()):
+        return None
+    blk = torch.as_tensor(_DevView(ptr, nbytes), device=device)
+    gathered = torch.empty(world * nbytes, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(gathered, blk)
+    torch.cuda.current_stream(device).synchronize()
+    try:
+        seq, d, counts = ix.batch_merge(gathered.data_ptr(), world, nbytes, np.asarray(bounds[:world], dtype=np.int64), nq, k)
+    except VsbError:
+        return None          # an entry log overflowed: the same verdict on every rank (same gathered data)
+    if implicit_rowids:
+        ids = seq + 1
+    else:
+        t = torch.from_numpy(ix.lookup_rowids(seq)).to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ids = t.cpu().numpy()
+    return [(ids[b, :counts[b]].copy(), d[b, :counts[b]].copy()) for b in range(nq)]

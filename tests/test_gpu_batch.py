@@ -73,3 +73,85 @@ def test_batch_fp_matches_single_query_path(oracle, vtype, metric):
             assert np.all(np.abs(res[b][1] - want_d) <= 2e-5 * scale)
             assert len(set(res[b][0].tolist()) ^ set(want_ids.tolist())) <= 2   # near ties may swap at the k-th place
         ix.close()
+
+
+def _sharded_batch(indexes, bounds, metric, q, k):
+    """the row-sharded batch path with the shards on ONE GPU: vsb_batch_shard_scan per shard, the blocks concatenated on
+    the device (what the NCCL all-gather does across GPUs), vsb_batch_merge, rowid lookup summed over the shards"""
+    import torch
+
+    from sqlite_vector_b200.shard import _DevView
+    world = len(indexes)
+    parts = []
+    for ix in indexes:
+        ptr, nbytes = ix.batch_shard_scan(metric, q, k)
+        parts.append(torch.as_tensor(_DevView(ptr, nbytes), device="cuda").clone())
+    gathered = torch.cat(parts)
+    torch.cuda.synchronize()
+    seq, d, counts = indexes[-1].batch_merge(gathered.data_ptr(), world, nbytes, np.asarray(bounds[:world], dtype=np.int64), q.shape[0], k)
+    ids = sum(ix.lookup_rowids(seq) for ix in indexes)
+    return [(ids[b, :counts[b]], d[b, :counts[b]]) for b in range(q.shape[0])]
+
+
+@pytest.mark.parametrize("vtype", [po.I8, po.U8])
+@pytest.mark.parametrize("metric", METRICS)
+def test_batch_row_sharded_bit_exact(oracle, vtype, metric):
+    """BASELINE config 4 in miniature: batched queries over 3 row shards == one scan over the whole column (heavy ties)"""
+    import sqlite_vector_b200 as vs
+    rng = np.random.Generator(np.random.PCG64(900 + 10 * vtype + metric))
+    for (n, dim, nq, k, lo_v, hi_v) in [(60000, 128, 40, 20, -3, 4), (45000, 256, 64, 100, -20, 21)]:
+        if vtype == po.U8:
+            lo_v, hi_v = 0, hi_v - lo_v
+        dt = np.int8 if vtype == po.I8 else np.uint8
+        x = rng.integers(lo_v, hi_v, (n, dim)).astype(dt)
+        q = rng.integers(lo_v, hi_v, (nq, dim)).astype(dt)
+        rowids = np.arange(n, dtype=np.int64) * 3 + 7
+        bounds = [0, n // 4 + 11, (2 * n) // 3, n]
+        shards = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            ix = vs.Index(vtype, dim, b - a, first_seq=a)
+            ix.append_dense(x[a:b], rowids[a:b])
+            ix.finalize()
+            shards.append(ix)
+        res = _sharded_batch(shards, bounds, metric, q, k)
+        whole = _index(vtype, x, rowids)
+        one = whole.scan_topk(metric, q, k)
+        for b in range(nq):
+            assert np.array_equal(res[b][0], one[b][0]) and np.array_equal(res[b][1], one[b][1]), (vtype, metric, n, b)
+        for b in (0, nq // 2, nq - 1):
+            want_ids, want_d = oracle.scan_dense(metric, vtype, q[b], x, rowids, k)
+            assert np.array_equal(res[b][0], want_ids) and np.array_equal(res[b][1], want_d), (vtype, metric, n, b)
+        for ix in shards + [whole]:
+            ix.close()
+
+
+def test_batch_row_sharded_fp_equals_single_shard():
+    import sqlite_vector_b200 as vs
+    rng = np.random.Generator(np.random.PCG64(77))
+    n, dim, nq, k = 50000, 768, 48, 20
+    x = po.convert(rng.standard_normal((n, dim), dtype=np.float32), po.BF16)
+    q = po.convert(rng.standard_normal((nq, dim), dtype=np.float32), po.BF16)
+    bounds = [0, 20000, n]
+    shards = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        ix = vs.Index(po.BF16, dim, b - a, first_seq=a)
+        ix.append_dense(x[a:b])
+        ix.finalize()
+        shards.append(ix)
+    whole = _index(po.BF16, x)
+    for metric in (po.DOT, po.COS, po.L2):
+        res = _sharded_batch(shards, bounds, metric, q, k)
+        one = whole.scan_topk(metric, q, k)
+        for b in range(nq):      # same refine arithmetic, same replay: identical, not merely close
+            assert np.array_equal(res[b][0], one[b][0]) and np.array_equal(res[b][1], one[b][1]), (metric, b)
+    for ix in shards + [whole]:
+        ix.close()
+
+
+def test_batch_shard_scan_refuses_what_the_batch_path_cannot_do():
+    import sqlite_vector_b200 as vs
+    x = np.zeros((20000, 16), dtype=np.float32)
+    ix = _index(po.F32, x)
+    with pytest.raises(vs.VsbError, match="no tensor-core batch path"):
+        ix.batch_shard_scan(po.L2, np.zeros((32, 16), dtype=np.float32), 5)
+    ix.close()

@@ -11,6 +11,7 @@ def main():
     ap.add_argument("--n", type=int, default=10_000_000); ap.add_argument("--dim", type=int, default=384)
     ap.add_argument("--vtype", type=int, default=api.I8); ap.add_argument("--metric", type=int, default=api.L2)
     ap.add_argument("--k", type=int, default=20); ap.add_argument("--nq", type=int, default=1024); ap.add_argument("--iters", type=int, default=3); ap.add_argument("--opts", type=str, default="")
+    ap.add_argument("--sweep", type=str, default="", help="';'-separated option sets (name=value,...) timed one after the other on the same corpus")
     a = ap.parse_args()
     eng = vs.load_engine()
     for kv in filter(None, a.opts.split(",")):
@@ -22,7 +23,11 @@ def main():
     elif a.vtype == api.U8: q = torch.clamp(torch.round(qs.abs() * 48), 0, 255).to(torch.uint8).cpu().numpy()
     elif a.vtype == api.BF16: q = qs.to(torch.bfloat16).view(torch.int16).cpu().numpy().view(np.uint16)
     else: q = qs.to(torch.float16).view(torch.int16).cpu().numpy().view(np.uint16)
-    for it in range(a.iters):
+    for cfg in (a.sweep.split(";") if a.sweep else [""]):
+      for kv in filter(None, cfg.split(",")):
+          name, val = kv.split("="); eng.set_option(name, int(val))
+      if cfg: print(f"--- {cfg}")
+      for it in range(a.iters):
         c0, k0 = ix.stat("batch_cands"), ix.stat("batch_kept")
         b0, u0 = ix.stat("batch_us"), ix.stat("tc_us")
         res = ix.scan_topk(a.metric, q, a.k)
