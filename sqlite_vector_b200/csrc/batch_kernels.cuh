@@ -133,6 +133,14 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *v) {
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Tile order.  Streaming mode (BSTAT=false): tile t = corpus-tile * NG + query-group, both operands streamed through
@@ -290,7 +298,8 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
             // small-K tiles; keeping the read pipe busy is what matters here).
             const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * N);
             auto issue = [&](int cb, uint32_t *v) {
-                tmem_ld32_nowait(tbase + (uint32_t)cb, v);
+                if constexpr (CH == 16) tmem_ld16_nowait(tbase + (uint32_t)cb, v);
+                else tmem_ld32_nowait(tbase + (uint32_t)cb, v);
                 if constexpr (CH == 64) {
                     if (cb + 32 < c_hi) tmem_ld32_nowait(tbase + (uint32_t)cb + 32, v + 32);
                 }
@@ -298,9 +307,10 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
             auto process = [&](int cb, const uint32_t *v) {
                 const bool two = (CH == 64) && (cb + 32) < c_hi;
                 const uint4 *qc4 = reinterpret_cast<const uint4 *>(qc_s + ng * N + cb);
+                constexpr int C0 = CH < 32 ? CH : 32;                          // columns in the first 32-column half
                 bool any0 = false, any1 = false;
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
+                for (int j4 = 0; j4 < C0 / 4; ++j4) {
                     const uint4 c = qc4[j4];
                     any0 |= tc_hit<INT8, MC>(v[4 * j4 + 0], c.x, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 1], c.y, rowf, rowi) |
                             tc_hit<INT8, MC>(v[4 * j4 + 2], c.z, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 3], c.w, rowf, rowi);
@@ -321,7 +331,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
                     uint32_t mask0 = 0, mask1 = 0;
                     if (any) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mask0 |= (tc_hit<INT8, MC>(v[j], qc[j], rowf, rowi) ? 1u : 0u) << j;
+                        for (int j = 0; j < C0; ++j) mask0 |= (tc_hit<INT8, MC>(v[j], qc[j], rowf, rowi) ? 1u : 0u) << j;
                         if constexpr (CH == 64) {
                             if (two) {
 #pragma unroll

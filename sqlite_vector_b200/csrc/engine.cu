@@ -37,7 +37,7 @@ int g_opt_ring_bytes = 0;      // 0: use all shared memory left
 int g_opt_no_batch = 0;        // 1: never take the tensor-core batch path
 int g_opt_batch_debug = 0;     // 1: print per-stage timings of the batch path to stderr (serialises the stages)
 int g_opt_bstat = 0;           // 1: park the query group in shared memory when it fits (measured: no gain, off by default)
-int g_opt_epi2 = 1;            // 1: tc_scan_kernel drains the accumulators with 8 epilogue warps (two per TMEM lane quadrant)
+int g_opt_epi2 = 2;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 2 = 8 epilogue warps, two per TMEM lane quadrant
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
 
 int fail(int code, const char *fmt, ...) {
