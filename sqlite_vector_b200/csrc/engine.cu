@@ -111,7 +111,7 @@ struct vsb_index {
     int num_sms = 0, max_smem = 0;
     // scan workspace
     int ws_kcap = 0, ws_logcap = 0, ws_streams = 0;
-    float *d_lists = nullptr;
+    float *d_lists = nullptr, *d_tlocal = nullptr;
     uint2 *d_logs = nullptr;
     int *d_counts = nullptr;
     Slot slot[kSlots];
@@ -232,11 +232,13 @@ int ensure_workspace(vsb_index *ix, int k) {
     if (ix->d_lists) cudaFree(ix->d_lists);
     if (ix->d_logs) cudaFree(ix->d_logs);
     if (ix->d_counts) cudaFree(ix->d_counts);
-    ix->d_lists = nullptr; ix->d_logs = nullptr; ix->d_counts = nullptr;
+    if (ix->d_tlocal) cudaFree(ix->d_tlocal);
+    ix->d_lists = nullptr; ix->d_logs = nullptr; ix->d_counts = nullptr; ix->d_tlocal = nullptr;
     ix->ws_kcap = 0;
     CU(cudaMalloc((void **)&ix->d_lists, sizeof(float) * (size_t)streams * kcap));
     CU(cudaMalloc((void **)&ix->d_logs, sizeof(uint2) * (size_t)streams * logcap));
     CU(cudaMalloc((void **)&ix->d_counts, sizeof(int) * (size_t)streams));
+    CU(cudaMalloc((void **)&ix->d_tlocal, sizeof(float) * (size_t)streams));
     ix->ws_kcap = kcap; ix->ws_logcap = logcap; ix->ws_streams = streams;
     return VSB_OK;
 }
@@ -266,6 +268,7 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
     p.k = k;
     p.kcap = kcap;
     p.lists = ix->d_lists;
+    p.tlocal = ix->d_tlocal;
     p.logs = ix->d_logs;
     p.counts = ix->d_counts;
     p.logcap = ix->ws_logcap;
@@ -295,6 +298,7 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         f.k = k;
         f.kcap = kcap;
         f.lists = ix->d_lists;
+        f.tlocal = ix->d_tlocal;
         f.logs = ix->d_logs;
         f.counts = ix->d_counts;
         f.logcap = ix->ws_logcap;
@@ -309,7 +313,7 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         const int nblocks = (f.S + kFilterWarps - 1) / kFilterWarps;
         slot->nblocks = nblocks;
         const size_t fsm_base = sizeof(float) * ((size_t)2 * kFilterWarps * kcap + (size_t)f.S + 32);
-        const size_t fsm_fast = fsm_base + sizeof(float) * (size_t)f.S * 32;
+        const size_t fsm_fast = fsm_base + sizeof(float) * (size_t)(f.S / kWarps) * 32;
         const bool fast = (k <= 32) && fsm_fast + 2048 <= (size_t)ix->max_smem;
         if (fast) {
             CU(cudaFuncSetAttribute((const void *)filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm_fast));
@@ -688,6 +692,7 @@ void vsb_index_free(vsb_index *ix) {
     if (ix->d_lists) cudaFree(ix->d_lists);
     if (ix->d_logs) cudaFree(ix->d_logs);
     if (ix->d_counts) cudaFree(ix->d_counts);
+    if (ix->d_tlocal) cudaFree(ix->d_tlocal);
     if (ix->d_dist_all) cudaFree(ix->d_dist_all);
     if (ix->d_vec) cudaFree(ix->d_vec);
     for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);

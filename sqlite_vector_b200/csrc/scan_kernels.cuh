@@ -44,7 +44,9 @@ struct ScanParams {
     int root;             // metric L2: take the square root
     int k;                // 0 => no top-k (dist_all only)
     int kcap;             // k rounded up to 32
-    float *lists;         // [streams][kcap]  k smallest distances of each stream (unsorted, +INF padded)
+    float *lists;         // k <= 32: [CTAs][32] the k smallest distances of each CTA's rows, sorted ascending, +INF padded;
+                          // k > 32:  [streams][kcap] k smallest distances of each stream (unsorted)
+    float *tlocal;        // k <= 32: [streams] k-th smallest distance over the EARLIER streams of the same CTA (+INF if < k rows)
     uint2 *logs;          // [streams][logcap] (dist bits, local row)
     int *counts;          // [streams] log entries written (may exceed logcap => overflow)
     int logcap;
@@ -294,6 +296,45 @@ __device__ __forceinline__ float warp_bitonic_merge_asc(float v, int lane) {
     return v;
 }
 
+__device__ __forceinline__ float funkey(uint32_t k) {  // inverse of fkey
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+// k <= 32: the warp's k-list lives in one register per lane, SORTED ascending (lanes >= k hold +INF); the running
+// k-th value is lane k-1.  Incoming lists are sorted too (scan_kernel publishes them that way), so an offer is either
+// a couple of shift-inserts or one bitonic merge — no serial chain of k inserts for the first streams of a segment.
+struct SortedList {
+    float v, thr;
+    int k;
+    __device__ __forceinline__ void init(int lane, int k_) { k = k_; v = INFINITY; thr = INFINITY; }
+    __device__ __forceinline__ void insert(int lane, float dv) {           // dv < thr
+        const int pos = __popc(__ballot_sync(0xFFFFFFFFu, v <= dv));       // elements that stay in front of dv
+        const float up = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+        v = (lane < pos) ? v : (lane == pos ? dv : up);
+        if (lane >= k) v = INFINITY;
+        thr = __shfl_sync(0xFFFFFFFFu, v, k - 1);
+    }
+    // val: a sorted ascending list, one value per lane, +INF padded
+    __device__ __forceinline__ void offer_sorted(int lane, float val) {
+        const int cnt = __popc(__ballot_sync(0xFFFFFFFFu, val < thr));     // these are the first cnt lanes
+        if (cnt == 0) return;
+        if (cnt <= 2) {
+            const float a = __shfl_sync(0xFFFFFFFFu, val, 0);
+            insert(lane, a);
+            if (cnt == 2) {
+                const float b = __shfl_sync(0xFFFFFFFFu, val, 1);
+                if (b < thr) insert(lane, b);
+            }
+            return;
+        }
+        // 32 smallest of the 64 values: min(L[i], R[31-i]) is bitonic; one merge network sorts it
+        const float rev = __shfl_sync(0xFFFFFFFFu, val, 31 - lane);
+        v = warp_bitonic_merge_asc(fminf(v, rev), lane);
+        if (lane >= k) v = INFINITY;
+        thr = __shfl_sync(0xFFFFFFFFu, v, k - 1);
+    }
+};
+
 // ------------------------------------------------------------------ the scan kernel
 template <int VT, int MC, bool DIRECT>
 __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm) {
@@ -440,17 +481,29 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
     if (topk) {
         __syncwarp();
         float *gl = prm.lists + (size_t)sidx * prm.kcap;
-        if (prm.kcap == 32) {
-            // k <= 32: publish the list sorted ascending, +INF padded (filter_kernel merges sorted lists in registers)
-            float v = (lane < prm.k) ? mylist[lane] : INFINITY;
-            v = warp_sort_asc(v, lane);
-            gl[lane] = v;
-        } else {
-            for (int j = lane; j < prm.kcap; j += 32) gl[j] = mylist[j];
-        }
         if (lane == 0) {
             prm.counts[sidx] = logged;
             if (logged > prm.logcap) atomicExch(&prm.ctrl[1], 1);
+        }
+        if (prm.kcap == 32) {
+            // k <= 32: the CTA's 8 streams are consecutive in scan order.  Sort each stream's list, then one warp merges
+            // them in stream order, recording the running k-th value BEFORE each stream (its in-CTA prefix bound), and
+            // publishes ONE sorted list per CTA: filter_kernel then walks 148 CTA lists instead of 1184 stream lists.
+            float v = (lane < prm.k) ? mylist[lane] : INFINITY;
+            v = warp_sort_asc(v, lane);
+            mylist[lane] = v;
+            __syncthreads();
+            if (warp == 0) {
+                SortedList L;
+                L.init(lane, prm.k);
+                for (int w = 0; w < kWarps; ++w) {
+                    if (lane == 0) prm.tlocal[(size_t)blockIdx.x * kWarps + w] = L.thr;
+                    L.offer_sorted(lane, lists_s[w * 32 + lane]);
+                }
+                prm.lists[(size_t)blockIdx.x * 32 + lane] = L.v;
+            }
+        } else {
+            for (int j = lane; j < prm.kcap; j += 32) gl[j] = mylist[j];
         }
     }
 }
@@ -464,7 +517,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
 struct FilterParams {
     int S;              // streams
     int k, kcap;
-    const float *lists; // [S][kcap]
+    const float *lists; // k <= 32: [S / kWarps][32] sorted CTA lists; else [S][kcap] stream lists
+    const float *tlocal;// k <= 32: [S] in-CTA prefix bound of each stream (from scan_kernel)
     const uint2 *logs;  // [S][logcap]
     const int *counts;  // [S]
     int logcap;
@@ -482,55 +536,17 @@ constexpr int kFilterWarps = 32;
 constexpr int kSegments = 8;  // threshold segments: few long serial walks beat many short ones (issue-bound otherwise)
 constexpr int kLogRegs = 8;   // log entries per lane prefetched into registers (256 per stream)
 
-__device__ __forceinline__ float funkey(uint32_t k) {  // inverse of fkey
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
-}
-
-// k <= 32: the warp's k-list lives in one register per lane, SORTED ascending (lanes >= k hold +INF); the running
-// k-th value is lane k-1.  Incoming lists are sorted too (scan_kernel publishes them that way), so an offer is either
-// a couple of shift-inserts or one bitonic merge — no serial chain of k inserts for the first streams of a segment.
-struct SortedList {
-    float v, thr;
-    int k;
-    __device__ __forceinline__ void init(int lane, int k_) { k = k_; v = INFINITY; thr = INFINITY; }
-    __device__ __forceinline__ void insert(int lane, float dv) {           // dv < thr
-        const int pos = __popc(__ballot_sync(0xFFFFFFFFu, v <= dv));       // elements that stay in front of dv
-        const float up = __shfl_up_sync(0xFFFFFFFFu, v, 1);
-        v = (lane < pos) ? v : (lane == pos ? dv : up);
-        if (lane >= k) v = INFINITY;
-        thr = __shfl_sync(0xFFFFFFFFu, v, k - 1);
-    }
-    // val: a sorted ascending list, one value per lane, +INF padded
-    __device__ __forceinline__ void offer_sorted(int lane, float val) {
-        const int cnt = __popc(__ballot_sync(0xFFFFFFFFu, val < thr));     // these are the first cnt lanes
-        if (cnt == 0) return;
-        if (cnt <= 2) {
-            const float a = __shfl_sync(0xFFFFFFFFu, val, 0);
-            insert(lane, a);
-            if (cnt == 2) {
-                const float b = __shfl_sync(0xFFFFFFFFu, val, 1);
-                if (b < thr) insert(lane, b);
-            }
-            return;
-        }
-        // 32 smallest of the 64 values: min(L[i], R[31-i]) is bitonic; one merge network sorts it
-        const float rev = __shfl_sync(0xFFFFFFFFu, val, 31 - lane);
-        v = warp_bitonic_merge_asc(fminf(v, rev), lane);
-        if (lane >= k) v = INFINITY;
-        thr = __shfl_sync(0xFFFFFFFFu, v, k - 1);
-    }
-};
-
-// FAST: k <= 32 and all S*k list values fit in shared memory (register lists, one L2 round trip).
+// FAST: k <= 32: scan_kernel published one sorted list per CTA plus each stream's in-CTA prefix bound; the lists are
+// merged in registers (one L2 round trip for 19 KB of lists).
 template <bool FAST>
 __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const FilterParams fp) {
     extern __shared__ __align__(16) uint8_t fsm[];
     const int k = fp.k, kcap = fp.kcap;
     float *seglist = reinterpret_cast<float *>(fsm);                        // [32][kcap] k smallest of each segment
     float *work = seglist + kFilterWarps * kcap;                            // [32][kcap] scratch (generic path)
-    float *tlocal = work + kFilterWarps * kcap;                             // [S] in-segment prefix threshold
+    float *tlocal = work + kFilterWarps * kcap;                             // [S] in-segment prefix threshold (FAST: per CTA)
     float *tseg = tlocal + fp.S;                                            // [32]
-    float *slists = tseg + 32;                                              // FAST: [S][k] copy of all stream lists
+    float *slists = tseg + 32;                                              // FAST: [S / kWarps][32] copy of the CTA lists
     __shared__ int wcount[kFilterWarps], woff[kFilterWarps];
     __shared__ int blk_base;
 
@@ -549,35 +565,23 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
         ereg[i] = (j < n_log) ? lg[j] : make_uint2(0x7FC00000u, 0u);       // NaN never survives
     }
 
+    const int ncta = fp.S / kWarps;                                         // scan CTAs (each published one sorted list)
     if constexpr (FAST) {
-        // all stream lists -> shared memory, fully parallel and coalesced
-        {   // all S x 32 list values -> shared memory.  Loads are issued in independent batches: a naive copy loop
-            // serialises on the LDG -> STS dependency (generic pointers may alias) and cost ~1 us per iteration.
-            const float4 *src = reinterpret_cast<const float4 *>(fp.lists);  // kcap == 32 on this path: lists are contiguous
+        const int GC = (ncta + kSegments - 1) / kSegments;                  // CTAs per segment
+        {   // all CTA lists (ncta x 32 floats, ~19 KB) -> shared memory in one coalesced pass
+            const float4 *src = reinterpret_cast<const float4 *>(fp.lists);
             float4 *dst = reinterpret_cast<float4 *>(slists);
-            const int tot4 = fp.S * 8;
-            for (int base = 0; base < tot4; base += kFilterWarps * 32 * 4) {
-                float4 tmp[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = base + u * kFilterWarps * 32 + (int)threadIdx.x;
-                    tmp[u] = (i < tot4) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = base + u * kFilterWarps * 32 + (int)threadIdx.x;
-                    if (i < tot4) dst[i] = tmp[u];
-                }
-            }
+            const int tot4 = ncta * 8;
+            for (int i = (int)threadIdx.x; i < tot4; i += kFilterWarps * 32) dst[i] = __ldg(src + i);
         }
         __syncthreads();
-        if (warp < kSegments) {   // phase 1: warp g walks segment g in stream order, recording the running k-th value before each stream
+        if (warp < kSegments) {   // phase 1: warp g walks the CTAs of segment g in order, recording the running k-th value before each CTA
             SortedList L;
             L.init(lane, k);
-            const int s0 = warp * G, s1 = min(fp.S, s0 + G);
-            for (int st = s0; st < s1; ++st) {
-                if (lane == 0) tlocal[st] = L.thr;
-                L.offer_sorted(lane, slists[st * 32 + lane]);
+            const int c0 = warp * GC, c1 = min(ncta, c0 + GC);
+            for (int c = c0; c < c1; ++c) {
+                if (lane == 0) tlocal[c] = L.thr;
+                L.offer_sorted(lane, slists[c * 32 + lane]);
             }
             seglist[warp * kcap + lane] = L.v;
         }
@@ -650,7 +654,14 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
 
     // ---- phase 3: count, reserve, write — survivors of this block's 32 streams in stream order
     float T = INFINITY;
-    if (s < fp.S) T = fminf(tlocal[s], tseg[s / G]);
+    if (s < fp.S) {
+        if constexpr (FAST) {
+            const int c = s / kWarps, GC = (ncta + kSegments - 1) / kSegments;
+            T = fminf(fminf(__ldg(fp.tlocal + s), tlocal[c]), tseg[c / GC]);
+        } else {
+            T = fminf(tlocal[s], tseg[s / G]);
+        }
+    }
     int mine = 0;
 #pragma unroll
     for (int i = 0; i < kLogRegs; ++i) mine += __popc(__ballot_sync(0xFFFFFFFFu, __uint_as_float(ereg[i].x) < T));
