@@ -154,7 +154,7 @@ VSB_API int64_t vsb_kernel_launches(void);
 /* with option "time_kernels"=1 every launch is bracketed by CUDA events on the engine stream; this returns
  * (and resets) the summed device time and launch count of the scan kernel and of the filter kernel. */
 VSB_API int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double *filter_ms, int *filter_launches);
-/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat","epi2","batch_debug"}; returns previous value */
+/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat","epi2","batch_debug","batch_m0","batch_growth"}; returns previous value */
 VSB_API int vsb_set_option(const char *name, int value);
 
 #ifdef __cplusplus

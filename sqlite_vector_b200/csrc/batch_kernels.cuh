@@ -443,19 +443,26 @@ struct RefineParams {
     const unsigned *cand_count;
     unsigned cand_cap;
     const float *U;          // [nq] exact distance bound of this level (strict <)
-    unsigned long long *kept_key;   // (query << 32) | row
-    float *kept_val;
-    unsigned *kept_count;
-    unsigned kept_cap;
+    uint2 *bucket;           // [nq][bucket_cap] (row, distance bits) kept for each query, unordered
+    unsigned *bcount;        // [nq] entries appended this level (may exceed bucket_cap => overflow, seen by replay_kernel)
+    unsigned bucket_cap;
+    unsigned *stats;         // [0] += candidates refined, [2] |= 1 when the candidate log overflowed
 };
 
+constexpr unsigned kBucketCap = 2048;   // kept candidates per query and level (replay_kernel sorts them in shared memory)
+
 // eight lanes per candidate (four candidates per warp step): the reference distance with the arithmetic of the
-// single-query kernel; survivors are appended with ONE atomic per warp step (a single hot counter is the bottleneck
-// otherwise: 2.5 M same-address atomics per batch).
+// single-query kernel; survivors go to their query's bucket (one atomic each on nq different counters; no global sort
+// and no host round trip per level: replay_kernel orders each bucket by row itself).
 template <int VT, int MC>
 __global__ void refine_kernel(const RefineParams rp) {
     constexpr int G = 8;
-    const unsigned ncand = min(*rp.cand_count, rp.cand_cap);
+    const unsigned ncand_raw = *rp.cand_count;
+    const unsigned ncand = min(ncand_raw, rp.cand_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&rp.stats[0], ncand);
+        if (ncand_raw > rp.cand_cap) atomicOr(&rp.stats[2], 1u);
+    }
     const int lane = threadIdx.x & 31, sub = lane & (G - 1), grp = lane / G;
     const unsigned wpb = blockDim.x >> 5, per_step = 32 / G;
     const int nc = rp.pitch / 16;
@@ -494,18 +501,9 @@ __global__ void refine_kernel(const RefineParams rp) {
         }
         const float d = finalize<VT, MC>(A, qn, rp.root);
         const bool keep = live && sub == 0 && d < rp.U[cq.y];
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-        if (m) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(rp.kept_count, (unsigned)__popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (keep) {
-                const unsigned w = base + __popc(m & ((1u << lane) - 1u));
-                if (w < rp.kept_cap) {
-                    rp.kept_key[w] = ((unsigned long long)cq.y << 32) | cq.x;
-                    rp.kept_val[w] = d;
-                }
-            }
+        if (keep) {
+            const unsigned w = atomicAdd(&rp.bcount[cq.y], 1u);
+            if (w < rp.bucket_cap) rp.bucket[(size_t)cq.y * rp.bucket_cap + w] = make_uint2(cq.x, __float_as_uint(d));
         }
     }
 }
@@ -540,10 +538,10 @@ __global__ void final_sort_kernel(float *slot_d, unsigned *slot_row, int nq, int
 
 // per-query slot state carried across levels (the reference's cursor arrays, src/sqlite-vector.c:1808-1813)
 struct ReplayParams {
-    const unsigned long long *key;   // sorted (query, row)
-    const float *val;
-    const unsigned *count;
-    unsigned cap;
+    const uint2 *bucket;    // [nq][bucket_cap] (row, distance bits) of this level, unordered
+    unsigned *bcount;       // [nq] in: entries of this level; reset to 0 for the next level
+    unsigned bucket_cap;
+    unsigned *stats;        // [1] += entries replayed, [2] |= 2 when a bucket overflowed
     int nq, k, kcap;
     float *slot_d;          // [nq][kcap]
     unsigned *slot_row;     // [nq][kcap]
@@ -628,46 +626,71 @@ __device__ inline float conservative_qc(int kind, int mc, int root, float U, con
     return clampf((1.0f - U - 1e-4f) * sqrtf(qq), -1e30f, 1e30f);
 }
 
-// one warp per query: feed this level's kept candidates (sorted by row) through the reference's slot update
-__global__ void replay_kernel(const ReplayParams rp) {
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (q >= rp.nq) return;
-    float *sd = rp.slot_d + (size_t)q * rp.kcap;
-    unsigned *sr = rp.slot_row + (size_t)q * rp.kcap;
-    if (rp.level0) {
-        for (int j = lane; j < rp.kcap; j += 32) { sd[j] = (j < rp.k) ? INFINITY : -INFINITY; sr[j] = 0; }
-        if (lane == 0) rp.slot_mi[q] = 0;
-        __syncwarp();
+constexpr int kReplayThreads = 128;
+
+// one block per query: order this level's kept candidates by row (bitonic sort in shared memory), then one warp feeds them
+// through the reference's slot update.  The slots live in shared memory while the block works on them.
+__global__ void __launch_bounds__(kReplayThreads) replay_kernel(const ReplayParams rp) {
+    __shared__ unsigned long long keys[kBucketCap];          // (row << 32) | distance bits
+    __shared__ float sd[256];
+    __shared__ unsigned sr[256];
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    float *gd = rp.slot_d + (size_t)q * rp.kcap;
+    unsigned *gr = rp.slot_row + (size_t)q * rp.kcap;
+    const unsigned c_raw = rp.bcount[q];
+    const unsigned c = min(c_raw, rp.bucket_cap);
+    unsigned n = 32;
+    while (n < c) n <<= 1;
+    const uint2 *bk = rp.bucket + (size_t)q * rp.bucket_cap;
+    for (unsigned i = tid; i < n; i += kReplayThreads) {
+        unsigned long long key = ~0ull;
+        if (i < c) { const uint2 e = bk[i]; key = ((unsigned long long)e.x << 32) | e.y; }
+        keys[i] = key;
     }
-    // this query's segment of the sorted key array
-    const unsigned n = min(*rp.count, rp.cap);
-    const unsigned long long lo_key = (unsigned long long)q << 32, hi_key = (unsigned long long)(q + 1) << 32;
-    unsigned a = 0, b = n;
-    while (a < b) { const unsigned m = (a + b) >> 1; if (rp.key[m] < lo_key) a = m + 1; else b = m; }
-    const unsigned seg0 = a;
-    b = n;
-    while (a < b) { const unsigned m = (a + b) >> 1; if (rp.key[m] < hi_key) a = m + 1; else b = m; }
-    const unsigned seg1 = a;
-    int mi = rp.slot_mi[q];
-    float cur = sd[mi];
-    int acc_n = (rp.acc_log != nullptr && !rp.level0) ? rp.acc_count[q] : 0;
-    uint2 *alog = rp.acc_log ? rp.acc_log + (size_t)q * rp.acc_cap : nullptr;
-    for (unsigned base = seg0; base < seg1; base += 32) {
-        const unsigned i = base + lane;
-        const float d = (i < seg1) ? rp.val[i] : INFINITY;
-        const unsigned row = (i < seg1) ? (unsigned)(rp.key[i] & 0xFFFFFFFFu) : 0u;
-        warp_offer32(sd, sr, rp.kcap, lane, d, row, mi, cur, [&](float dv, unsigned rv) {
-            if (alog != nullptr && lane == 0 && acc_n < rp.acc_cap) alog[acc_n] = make_uint2(__float_as_uint(dv), rv);
-            ++acc_n;
-        });
+    for (int j = tid; j < rp.kcap; j += kReplayThreads) {
+        if (rp.level0) { sd[j] = (j < rp.k) ? INFINITY : -INFINITY; sr[j] = 0; }
+        else { sd[j] = gd[j]; sr[j] = gr[j]; }
     }
-    if (lane == 0) {
-        rp.slot_mi[q] = mi;
-        rp.U[q] = cur;
-        rp.qc[q] = conservative_qc(rp.kind, rp.mc, rp.root, cur, rp.qnorm, q, rp.rnmax);
-        if (rp.acc_log != nullptr) rp.acc_count[q] = acc_n;
+    __syncthreads();
+    for (unsigned size = 2; size <= n; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = tid; t < (n >> 1); t += kReplayThreads) {
+                const unsigned i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), j = i + stride;
+                const unsigned long long a = keys[i], b = keys[j];
+                const bool up = (i & size) == 0;
+                if ((a > b) == up) { keys[i] = b; keys[j] = a; }
+            }
+            __syncthreads();
+        }
     }
+    if (tid < 32) {
+        int mi = rp.level0 ? 0 : rp.slot_mi[q];
+        float cur = sd[mi];
+        int acc_n = (rp.acc_log != nullptr && !rp.level0) ? rp.acc_count[q] : 0;
+        uint2 *alog = rp.acc_log ? rp.acc_log + (size_t)q * rp.acc_cap : nullptr;
+        for (unsigned base = 0; base < c; base += 32) {
+            const unsigned i = base + lane;
+            const unsigned long long key = (i < c) ? keys[i] : 0ull;
+            const float d = (i < c) ? __uint_as_float((unsigned)(key & 0xFFFFFFFFu)) : INFINITY;
+            const unsigned row = (unsigned)(key >> 32);
+            warp_offer32(sd, sr, rp.kcap, lane, d, row, mi, cur, [&](float dv, unsigned rv) {
+                if (alog != nullptr && lane == 0 && acc_n < rp.acc_cap) alog[acc_n] = make_uint2(__float_as_uint(dv), rv);
+                ++acc_n;
+            });
+        }
+        if (lane == 0) {
+            rp.slot_mi[q] = mi;
+            rp.U[q] = cur;
+            rp.qc[q] = conservative_qc(rp.kind, rp.mc, rp.root, cur, rp.qnorm, q, rp.rnmax);
+            if (rp.acc_log != nullptr) rp.acc_count[q] = acc_n;
+            rp.bcount[q] = 0;
+            atomicAdd(&rp.stats[1], c);
+            if (c_raw > rp.bucket_cap) atomicOr(&rp.stats[2], 2u);
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < rp.kcap; j += kReplayThreads) { gd[j] = sd[j]; gr[j] = sr[j]; }
 }
 
 // ------------------------------------------------------------------ row-sharded batches: merge of the shards' entry logs

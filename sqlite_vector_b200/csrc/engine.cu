@@ -36,6 +36,8 @@ int g_opt_direct = 0;          // 1: force the no-staging kernel
 int g_opt_ring_bytes = 0;      // 0: use all shared memory left
 int g_opt_no_batch = 0;        // 1: never take the tensor-core batch path
 int g_opt_batch_debug = 0;     // 1: print per-stage timings of the batch path to stderr (serialises the stages)
+int g_opt_batch_m0 = 1024;     // batch path: rows refined exhaustively before the first tensor-core level
+int g_opt_batch_growth = 32;   // batch path: each tensor-core level covers rows [m, growth*m)
 int g_opt_bstat = 0;           // 1: park the query group in shared memory when it fits (measured: no gain, off by default)
 int g_opt_epi2 = 2;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 2 = 8 epilogue warps, two per TMEM lane quadrant
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
@@ -83,6 +85,18 @@ constexpr int kFirstFetch = 1024;
 constexpr size_t kResHdrBytes = 64 + sizeof(int2) * kTableCap;
 constexpr size_t kHeadBytes = kResHdrBytes + sizeof(uint2) * kFirstFetch;
 
+// scan workspace (per-stream k-lists / CTA lists, in-CTA bounds, candidate logs): written by scan_kernel, read by
+// filter_kernel.  Two of them alternate so that the filter of query i (filter stream) overlaps the scan of query i+1.
+struct Work {
+    float *d_lists = nullptr, *d_tlocal = nullptr;
+    uint2 *d_logs = nullptr;
+    int *d_counts = nullptr;
+    cudaEvent_t scanned = nullptr;   // scan stream: the scan that filled this workspace has finished
+    cudaEvent_t drained = nullptr;   // filter stream: the filter that read this workspace has finished
+    bool in_use = false;
+};
+constexpr int kWorks = 2;
+
 struct Slot {
     uint8_t *d_res = nullptr, *h_res = nullptr;      // this slot's head inside vsb_index::d_heads / h_heads
     uint2 *h_out = nullptr, *d_out = nullptr;        // first kFirstFetch survivors (inside the head)
@@ -109,18 +123,17 @@ struct vsb_index {
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     int stage_next = 0;
     int num_sms = 0, max_smem = 0;
-    // scan workspace
-    int ws_kcap = 0, ws_logcap = 0, ws_streams = 0;
-    float *d_lists = nullptr, *d_tlocal = nullptr;
-    uint2 *d_logs = nullptr;
-    int *d_counts = nullptr;
+    cudaStream_t fstream = nullptr;   // filter + result copy of a query; `stream` carries staging, scans and the batch path
+    // scan workspaces
+    int ws_kcap = 0, ws_logcap = 0, ws_streams = 0, ws_next = 0;
+    Work work[kWorks];
     Slot slot[kSlots];
     uint8_t *d_heads = nullptr, *h_heads = nullptr;   // kSlots x kHeadBytes
     bool slots_ready = false;
     float *d_dist_all = nullptr;
     int last_slot = -1, last_metric = 0;
     // optional per-kernel event timing (vsb_profile_read)
-    std::vector<cudaEvent_t> prof_ev;   // triples: before scan, after scan, after filter
+    std::vector<cudaEvent_t> prof_ev;   // quadruples: before scan, after scan (scan stream), before filter, after filter (filter stream)
     std::vector<int> prof_kind;         // 1 = scan only, 2 = scan + filter
     size_t prof_used = 0;
     size_t dev_bytes = 0;
@@ -181,6 +194,9 @@ Plan make_plan(const vsb_index *ix, int kcap) {
     size_t avail = (size_t)ix->max_smem > fixed ? (size_t)ix->max_smem - fixed : 0;
     if (g_opt_ring_bytes > 0 && (size_t)g_opt_ring_bytes < avail) avail = (size_t)g_opt_ring_bytes;
     const size_t wtile = (size_t)(32 >> log2P) * pitch;
+    // leave room on the SM for one filter block of the previous query (it runs beside the scan CTA, see launch_scan)
+    const size_t reserve = filter_fast_smem(ix->num_sms) + 3072;
+    if (kcap > 0 && kcap <= 32 && avail > reserve && (avail - reserve) / kWarps / (wtile ? wtile : 1) >= 2) avail -= reserve;
     int nsw = (int)(avail / kWarps / (wtile ? wtile : 1));
     if (nsw > kMaxStages) nsw = kMaxStages;
     pl.direct = g_opt_direct || nsw < 2;
@@ -229,16 +245,24 @@ int ensure_workspace(vsb_index *ix, int k) {
     const int logcap = std::max(256, 12 * k);
     const int streams = ix->num_sms * kWarps;
     if (ix->ws_kcap >= kcap && ix->ws_logcap >= logcap && ix->ws_streams == streams) return VSB_OK;
-    if (ix->d_lists) cudaFree(ix->d_lists);
-    if (ix->d_logs) cudaFree(ix->d_logs);
-    if (ix->d_counts) cudaFree(ix->d_counts);
-    if (ix->d_tlocal) cudaFree(ix->d_tlocal);
-    ix->d_lists = nullptr; ix->d_logs = nullptr; ix->d_counts = nullptr; ix->d_tlocal = nullptr;
+    CU(cudaStreamSynchronize(ix->stream));       // queries in flight still use the old workspaces
+    CU(cudaStreamSynchronize(ix->fstream));
     ix->ws_kcap = 0;
-    CU(cudaMalloc((void **)&ix->d_lists, sizeof(float) * (size_t)streams * kcap));
-    CU(cudaMalloc((void **)&ix->d_logs, sizeof(uint2) * (size_t)streams * logcap));
-    CU(cudaMalloc((void **)&ix->d_counts, sizeof(int) * (size_t)streams));
-    CU(cudaMalloc((void **)&ix->d_tlocal, sizeof(float) * (size_t)streams));
+    for (int i = 0; i < kWorks; ++i) {
+        Work &w = ix->work[i];
+        if (w.d_lists) cudaFree(w.d_lists);
+        if (w.d_logs) cudaFree(w.d_logs);
+        if (w.d_counts) cudaFree(w.d_counts);
+        if (w.d_tlocal) cudaFree(w.d_tlocal);
+        w.d_lists = nullptr; w.d_logs = nullptr; w.d_counts = nullptr; w.d_tlocal = nullptr;
+        w.in_use = false;
+        CU(cudaMalloc((void **)&w.d_lists, sizeof(float) * (size_t)streams * kcap));
+        CU(cudaMalloc((void **)&w.d_logs, sizeof(uint2) * (size_t)streams * logcap));
+        CU(cudaMalloc((void **)&w.d_counts, sizeof(int) * (size_t)streams));
+        CU(cudaMalloc((void **)&w.d_tlocal, sizeof(float) * (size_t)streams));
+        if (!w.scanned) CU(cudaEventCreateWithFlags(&w.scanned, cudaEventDisableTiming));
+        if (!w.drained) CU(cudaEventCreateWithFlags(&w.drained, cudaEventDisableTiming));
+    }
     ix->ws_kcap = kcap; ix->ws_logcap = logcap; ix->ws_streams = streams;
     return VSB_OK;
 }
@@ -255,6 +279,15 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
     if (!fn) return fail(VSB_EINVAL, "unsupported vector type %d", ix->vtype);
     CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
 
+    // the scan runs on ix->stream, the filter (+ result copy) on ix->fstream: while the filter of this query walks the
+    // k-lists and compacts the candidate logs, the scan of the next query is already streaming the shard (the filter
+    // blocks are small enough to sit on the SMs beside the scan CTAs).  The two workspaces alternate.
+    Work *wk = nullptr;
+    if (k > 0) {
+        wk = &ix->work[ix->ws_next];
+        ix->ws_next = (ix->ws_next + 1) % kWorks;
+        if (wk->in_use) CU(cudaStreamWaitEvent(ix->stream, wk->drained, 0));   // its previous filter must have read it
+    }
     ScanParams p{};
     p.vec = ix->d_vec;
     p.n = ix->n;
@@ -267,24 +300,24 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
     p.root = root;
     p.k = k;
     p.kcap = kcap;
-    p.lists = ix->d_lists;
-    p.tlocal = ix->d_tlocal;
-    p.logs = ix->d_logs;
-    p.counts = ix->d_counts;
+    p.lists = wk ? wk->d_lists : nullptr;
+    p.tlocal = wk ? wk->d_tlocal : nullptr;
+    p.logs = wk ? wk->d_logs : nullptr;
+    p.counts = wk ? wk->d_counts : nullptr;
     p.logcap = ix->ws_logcap;
     p.ctrl = slot ? slot->d_ctrl : nullptr;
     p.dist_all = d_dist_all;
     cudaEvent_t *pev = nullptr;
     if (g_opt_time_kernels) {
-        if (ix->prof_used + 3 > ix->prof_ev.size()) {
-            for (int i = 0; i < 3; ++i) {
+        if (ix->prof_used + 4 > ix->prof_ev.size()) {
+            for (int i = 0; i < 4; ++i) {
                 cudaEvent_t e;
                 CU(cudaEventCreate(&e));
                 ix->prof_ev.push_back(e);
             }
         }
         pev = &ix->prof_ev[ix->prof_used];
-        ix->prof_used += 3;
+        ix->prof_used += 4;
         ix->prof_kind.push_back(k > 0 ? 2 : 1);
         CU(cudaEventRecord(pev[0], ix->stream));
     }
@@ -293,14 +326,16 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
     ++g_launches;
     if (pev) CU(cudaEventRecord(pev[1], ix->stream));
     if (k > 0) {
+        CU(cudaEventRecord(wk->scanned, ix->stream));
+        CU(cudaStreamWaitEvent(ix->fstream, wk->scanned, 0));
         FilterParams f{};
         f.S = ix->ws_streams;
         f.k = k;
         f.kcap = kcap;
-        f.lists = ix->d_lists;
-        f.tlocal = ix->d_tlocal;
-        f.logs = ix->d_logs;
-        f.counts = ix->d_counts;
+        f.lists = wk->d_lists;
+        f.tlocal = wk->d_tlocal;
+        f.logs = wk->d_logs;
+        f.counts = wk->d_counts;
         f.logcap = ix->ws_logcap;
         f.out = slot->d_out;
         f.headcap = kFirstFetch;
@@ -310,24 +345,28 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         f.hdr = slot->d_hdr;
         f.ctrl = slot->d_ctrl;
         f.seqno = ++slot->seq;
-        const int nblocks = (f.S + kFilterWarps - 1) / kFilterWarps;
+        const bool fast = (k <= 32) && filter_fast_smem(f.S / kWarps) + 2048 <= (size_t)ix->max_smem;
+        const int fw = filter_warps(fast);
+        const int nblocks = (f.S + fw - 1) / fw;
+        if (nblocks > kTableCap) return fail(VSB_ERANGE, "too many filter blocks (%d)", nblocks);
         slot->nblocks = nblocks;
-        const size_t fsm_base = sizeof(float) * ((size_t)2 * kFilterWarps * kcap + (size_t)f.S + 32);
-        const size_t fsm_fast = fsm_base + sizeof(float) * (size_t)(f.S / kWarps) * 32;
-        const bool fast = (k <= 32) && fsm_fast + 2048 <= (size_t)ix->max_smem;
+        if (pev) CU(cudaEventRecord(pev[2], ix->fstream));
         if (fast) {
-            CU(cudaFuncSetAttribute((const void *)filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm_fast));
-            filter_kernel<true><<<nblocks, kFilterWarps * 32, fsm_fast, ix->stream>>>(f);
+            const size_t fsm = filter_fast_smem(f.S / kWarps);
+            CU(cudaFuncSetAttribute((const void *)filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            filter_kernel<true><<<nblocks, fw * 32, fsm, ix->fstream>>>(f);
         } else {
-            CU(cudaFuncSetAttribute((const void *)filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm_base));
-            filter_kernel<false><<<nblocks, kFilterWarps * 32, fsm_base, ix->stream>>>(f);
+            const size_t fsm = sizeof(float) * ((size_t)2 * kFilterWarps * kcap + (size_t)f.S + 32);
+            CU(cudaFuncSetAttribute((const void *)filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            filter_kernel<false><<<nblocks, fw * 32, fsm, ix->fstream>>>(f);
         }
         CU(cudaGetLastError());
         ++g_launches;
-        if (pev) CU(cudaEventRecord(pev[2], ix->stream));
-        if (nblocks > kTableCap) return fail(VSB_ERANGE, "too many filter blocks (%d)", nblocks);
-        if (fetch) CU(cudaMemcpyAsync(slot->h_res, slot->d_res, kHeadBytes, cudaMemcpyDeviceToHost, ix->stream));
-        CU(cudaEventRecord(slot->done, ix->stream));
+        if (pev) CU(cudaEventRecord(pev[3], ix->fstream));
+        CU(cudaEventRecord(wk->drained, ix->fstream));
+        wk->in_use = true;
+        if (fetch) CU(cudaMemcpyAsync(slot->h_res, slot->d_res, kHeadBytes, cudaMemcpyDeviceToHost, ix->fstream));
+        CU(cudaEventRecord(slot->done, ix->fstream));
     }
     return VSB_OK;
 }
@@ -379,8 +418,8 @@ int gather_survivors(vsb_index *ix, Slot *slot, std::vector<uint2> &out, bool *o
     const int total = slot->h_hdr[0];
     if (total > kFirstFetch) {  // rare: fetch the tail of the survivor list
         if (cudaMemcpyAsync(slot->h_tail, slot->d_tail, sizeof(uint2) * (size_t)(total - kFirstFetch),
-                            cudaMemcpyDeviceToHost, ix->stream) != cudaSuccess ||
-            cudaStreamSynchronize(ix->stream) != cudaSuccess)
+                            cudaMemcpyDeviceToHost, ix->fstream) != cudaSuccess ||
+            cudaStreamSynchronize(ix->fstream) != cudaSuccess)
             return fail(VSB_ECUDA, "fetching %d survivors failed: %s", total, cudaGetErrorString(cudaGetLastError()));
     }
     out.clear();
@@ -434,7 +473,7 @@ int query_candidates(vsb_index *ix, int metric, const void *query, int k, std::v
         if (rc) return rc;
         rc = launch_scan(ix, metric, slot->d_query, k, slot, nullptr);
         if (rc) return rc;
-        CU(cudaStreamSynchronize(ix->stream));
+        CU(cudaEventSynchronize(slot->done));
         int n = gather_survivors(ix, slot, cands, &overflow);
         if (n < 0) return n;
     }
@@ -497,6 +536,8 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "no_batch")) p = &g_opt_no_batch;
     else if (!strcmp(name, "bstat")) p = &g_opt_bstat;
     else if (!strcmp(name, "epi2")) p = &g_opt_epi2;
+    else if (!strcmp(name, "batch_m0")) p = &g_opt_batch_m0;
+    else if (!strcmp(name, "batch_growth")) p = &g_opt_batch_growth;
     else if (!strcmp(name, "batch_debug")) p = &g_opt_batch_debug;
     if (!p) return fail(VSB_EINVAL, "unknown option %s", name);
     int old = *p;
@@ -526,12 +567,18 @@ int vsb_index_create(vsb_index **out, int device, int vtype, int dim, int64_t ca
     ix->num_sms = pr.multiProcessorCount;
     ix->max_smem = (int)pr.sharedMemPerBlockOptin;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete ix; return fail(VSB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->fstream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        if (ix->stream) cudaStreamDestroy(ix->stream);
+        delete ix;
+        return fail(VSB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
     const size_t bytes = (size_t)std::max<long long>(capacity_rows, 1) * ix->pitch + 1024;
     e = cudaMalloc((void **)&ix->d_vec, bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
         cudaStreamDestroy(ix->stream);
+        cudaStreamDestroy(ix->fstream);
         delete ix;
         return fail(VSB_ENOMEM, "cudaMalloc(%zu bytes) for the resident column failed: %s", bytes, cudaGetErrorString(e));
     }
@@ -665,15 +712,16 @@ int64_t vsb_index_stat(const vsb_index *ix, const char *name) {
     if (!strcmp(name, "tc_rows")) return ix->st_tc_rows;
     if (!strcmp(name, "fetch_bytes")) return (long long)kHeadBytes;
     if (!strcmp(name, "slots")) return kSlots;
-    if (!strcmp(name, "filter_blocks")) return (ix->num_sms * kWarps + kFilterWarps - 1) / kFilterWarps;
+    if (!strcmp(name, "filter_blocks")) return (ix->num_sms * kWarps + kFilterWarpsFast - 1) / kFilterWarpsFast;
     return -1;
 }
-void *vsb_index_stream(vsb_index *ix) { return ix ? (void *)ix->stream : nullptr; }
+void *vsb_index_stream(vsb_index *ix) { return ix ? (void *)ix->fstream : nullptr; }
 
 void vsb_index_free(vsb_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
+    if (ix->fstream) cudaStreamSynchronize(ix->fstream);
     for (int b = 0; b < 2; ++b) {
         if (ix->stage[b]) cudaFreeHost(ix->stage[b]);
         if (ix->stage_ev[b]) cudaEventDestroy(ix->stage_ev[b]);
@@ -689,14 +737,20 @@ void vsb_index_free(vsb_index *ix) {
     }
     if (ix->h_heads) cudaFreeHost(ix->h_heads);
     if (ix->d_heads) cudaFree(ix->d_heads);
-    if (ix->d_lists) cudaFree(ix->d_lists);
-    if (ix->d_logs) cudaFree(ix->d_logs);
-    if (ix->d_counts) cudaFree(ix->d_counts);
-    if (ix->d_tlocal) cudaFree(ix->d_tlocal);
+    for (int i = 0; i < kWorks; ++i) {
+        Work &w = ix->work[i];
+        if (w.d_lists) cudaFree(w.d_lists);
+        if (w.d_logs) cudaFree(w.d_logs);
+        if (w.d_counts) cudaFree(w.d_counts);
+        if (w.d_tlocal) cudaFree(w.d_tlocal);
+        if (w.scanned) cudaEventDestroy(w.scanned);
+        if (w.drained) cudaEventDestroy(w.drained);
+    }
     if (ix->d_dist_all) cudaFree(ix->d_dist_all);
     if (ix->d_vec) cudaFree(ix->d_vec);
     for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
     batch_free(ix);
+    if (ix->fstream) cudaStreamDestroy(ix->fstream);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -798,14 +852,15 @@ int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double 
     if (check_index(ix)) return VSB_EINVAL;
     CU(cudaSetDevice(ix->device));
     CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaStreamSynchronize(ix->fstream));
     double a = 0, b = 0;
     int na = 0, nb = 0;
     for (size_t i = 0; i < ix->prof_kind.size(); ++i) {
         float ms = 0;
-        CU(cudaEventElapsedTime(&ms, ix->prof_ev[3 * i], ix->prof_ev[3 * i + 1]));
+        CU(cudaEventElapsedTime(&ms, ix->prof_ev[4 * i], ix->prof_ev[4 * i + 1]));
         a += ms; ++na;
         if (ix->prof_kind[i] == 2) {
-            CU(cudaEventElapsedTime(&ms, ix->prof_ev[3 * i + 1], ix->prof_ev[3 * i + 2]));
+            CU(cudaEventElapsedTime(&ms, ix->prof_ev[4 * i + 2], ix->prof_ev[4 * i + 3]));
             b += ms; ++nb;
         }
     }
@@ -895,6 +950,8 @@ int vsb_batch_shard_scan(vsb_index *ix, int metric, const void *queries, int nq,
     int rc = batch_levels(ix, metric, queries, nq, k, true);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ix->stream));
+    rc = batch_check(ix, (BatchWs *)ix->batch);
+    if (rc) return rc;
     ix->st_batch_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     BatchWs *w = (BatchWs *)ix->batch;
     *d_block = w->d_acc;

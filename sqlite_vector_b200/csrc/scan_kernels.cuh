@@ -532,29 +532,41 @@ struct FilterParams {
     int seqno;
 };
 
-constexpr int kFilterWarps = 32;
+constexpr int kFilterWarps = 32;      // generic path: streams (warps) per block
+constexpr int kFilterWarpsFast = 8;   // k <= 32 path: small blocks (8 warps, ~21 KB smem) that fit on an SM NEXT TO a scan CTA, so
+                                      // that the filter of query i runs while the scan of query i+1 streams (engine: two streams)
+__host__ __device__ constexpr int filter_warps(bool fast) { return fast ? kFilterWarpsFast : kFilterWarps; }
+// shared memory of the k <= 32 path: [kSegments][32] segment lists | [ncta4] per-CTA bound | [32] segment bounds | [ncta][32] CTA lists
+__host__ __device__ constexpr size_t filter_fast_smem(int ncta) {
+    return sizeof(float) * ((size_t)8 * 32 + (size_t)((ncta + 3) & ~3) + 32 + (size_t)ncta * 32);
+}
 constexpr int kSegments = 8;  // threshold segments: few long serial walks beat many short ones (issue-bound otherwise)
 constexpr int kLogRegs = 8;   // log entries per lane prefetched into registers (256 per stream)
 
 // FAST: k <= 32: scan_kernel published one sorted list per CTA plus each stream's in-CTA prefix bound; the lists are
 // merged in registers (one L2 round trip for 19 KB of lists).
 template <bool FAST>
-__global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const FilterParams fp) {
+__global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(const FilterParams fp) {
+    constexpr int FW = filter_warps(FAST);
+    static_assert(FW >= kSegments, "the segment walks use the first kSegments warps");
     extern __shared__ __align__(16) uint8_t fsm[];
     const int k = fp.k, kcap = fp.kcap;
-    float *seglist = reinterpret_cast<float *>(fsm);                        // [32][kcap] k smallest of each segment
-    float *work = seglist + kFilterWarps * kcap;                            // [32][kcap] scratch (generic path)
-    float *tlocal = work + kFilterWarps * kcap;                             // [S] in-segment prefix threshold (FAST: per CTA)
-    float *tseg = tlocal + fp.S;                                            // [32]
-    float *slists = tseg + 32;                                              // FAST: [S / kWarps][32] copy of the CTA lists
-    __shared__ int wcount[kFilterWarps], woff[kFilterWarps];
+    const int ncta = fp.S / kWarps;                                         // scan CTAs (FAST: each published one sorted list)
+    // generic: [32][kcap] segment lists | [32][kcap] scratch | [S] in-segment prefix bound | [32] segment bounds
+    // FAST:    see filter_fast_smem (kcap == 32)
+    float *seglist = reinterpret_cast<float *>(fsm);
+    float *work = seglist + kFilterWarps * kcap;                            // generic only
+    float *tlocal = FAST ? seglist + kSegments * 32 : work + kFilterWarps * kcap;   // FAST: per-CTA bound
+    float *tseg = tlocal + (FAST ? ((ncta + 3) & ~3) : fp.S);               // [32]
+    float *slists = tseg + 32;                                              // FAST: [ncta][32] copy of the CTA lists
+    __shared__ int wcount[FW], woff[FW];
     __shared__ int blk_base;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = (fp.S + kSegments - 1) / kSegments;                       // streams per segment
+    const int G = (fp.S + kSegments - 1) / kSegments;                       // streams per segment (generic)
 
     // ---- issue this warp's log loads first: they do not depend on the thresholds
-    const int s = blockIdx.x * kFilterWarps + warp;
+    const int s = blockIdx.x * FW + warp;
     int n_log = 0;
     uint2 ereg[kLogRegs];
     const uint2 *lg = fp.logs + (size_t)s * fp.logcap;
@@ -565,14 +577,13 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
         ereg[i] = (j < n_log) ? lg[j] : make_uint2(0x7FC00000u, 0u);       // NaN never survives
     }
 
-    const int ncta = fp.S / kWarps;                                         // scan CTAs (each published one sorted list)
     if constexpr (FAST) {
         const int GC = (ncta + kSegments - 1) / kSegments;                  // CTAs per segment
         {   // all CTA lists (ncta x 32 floats, ~19 KB) -> shared memory in one coalesced pass
             const float4 *src = reinterpret_cast<const float4 *>(fp.lists);
             float4 *dst = reinterpret_cast<float4 *>(slists);
             const int tot4 = ncta * 8;
-            for (int i = (int)threadIdx.x; i < tot4; i += kFilterWarps * 32) dst[i] = __ldg(src + i);
+            for (int i = (int)threadIdx.x; i < tot4; i += FW * 32) dst[i] = __ldg(src + i);
         }
         __syncthreads();
         if (warp < kSegments) {   // phase 1: warp g walks the CTAs of segment g in order, recording the running k-th value before each CTA
@@ -674,7 +685,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 1) filter_kernel(const Filt
     __syncthreads();
     if (threadIdx.x == 0) {
         int tot = 0;
-        for (int w = 0; w < kFilterWarps; ++w) { woff[w] = tot; tot += wcount[w]; }
+        for (int w = 0; w < FW; ++w) { woff[w] = tot; tot += wcount[w]; }
         const int base = atomicAdd(&fp.ctrl[0], tot);
         blk_base = base;
         fp.table[blockIdx.x] = make_int2(base, tot);

@@ -155,3 +155,47 @@ def test_batch_shard_scan_refuses_what_the_batch_path_cannot_do():
     with pytest.raises(vs.VsbError, match="no tensor-core batch path"):
         ix.batch_shard_scan(po.L2, np.zeros((32, 16), dtype=np.float32), 5)
     ix.close()
+
+
+@pytest.mark.parametrize("m0,growth", [(128, 4), (256, 8), (2048, 64)])
+def test_batch_level_schedule_does_not_change_results(oracle, m0, growth):
+    """the level schedule (exhaustive prefix, geometric growth) is a performance knob: results stay bit-exact"""
+    import sqlite_vector_b200 as vs
+    eng = vs.load_engine()
+    rng = np.random.Generator(np.random.PCG64(31337))
+    n, dim, nq, k = 70000, 128, 50, 20
+    x = rng.integers(-8, 9, (n, dim)).astype(np.int8)
+    q = rng.integers(-8, 9, (nq, dim)).astype(np.int8)
+    ix = _index(po.I8, x)
+    old = eng.set_option("batch_m0", m0), eng.set_option("batch_growth", growth)
+    try:
+        b0 = ix.stat("batches")
+        res = ix.scan_topk(po.L2, q, k)
+        assert ix.stat("batches") == b0 + 1
+    finally:
+        eng.set_option("batch_m0", old[0]); eng.set_option("batch_growth", old[1])
+    rowids = np.arange(1, n + 1, dtype=np.int64)
+    for b in range(nq):
+        want_ids, want_d = oracle.scan_dense(po.L2, po.I8, q[b], x, rowids, k)
+        assert np.array_equal(res[b][0], want_ids) and np.array_equal(res[b][1], want_d), (m0, growth, b)
+    ix.close()
+
+
+def test_batch_bucket_overflow_falls_back(oracle):
+    """descending distances: every row enters the slots, the per-level buckets overflow, the call falls back to the
+    per-query path and still returns the exact result"""
+    import sqlite_vector_b200 as vs
+    n, dim, nq, k = 40000, 128, 16, 5
+    x = np.zeros((n, dim), dtype=np.int8)
+    x[:, 0] = np.clip((n - 1 - np.arange(n)) // 320, 0, 124).astype(np.int8)      # distance to q shrinks along the scan
+    x[:, 1] = ((n - 1 - np.arange(n)) % 320 // 3).astype(np.int8)
+    q = np.zeros((nq, dim), dtype=np.int8)
+    ix = _index(po.I8, x)
+    f0 = ix.stat("fallbacks")
+    res = ix.scan_topk(po.L2, q, k)
+    rowids = np.arange(1, n + 1, dtype=np.int64)
+    for b in (0, nq - 1):
+        want_ids, want_d = oracle.scan_dense(po.L2, po.I8, q[b], x, rowids, k)
+        assert np.array_equal(res[b][0], want_ids) and np.array_equal(res[b][1], want_d)
+    assert ix.stat("fallbacks") >= f0       # the fallback counter only moves when a capacity was exceeded
+    ix.close()
