@@ -36,8 +36,8 @@ int g_opt_direct = 0;          // 1: force the no-staging kernel
 int g_opt_ring_bytes = 0;      // 0: use all shared memory left
 int g_opt_no_batch = 0;        // 1: never take the tensor-core batch path
 int g_opt_batch_debug = 0;     // 1: print per-stage timings of the batch path to stderr (serialises the stages)
-int g_opt_batch_m0 = 1024;     // batch path: rows refined exhaustively before the first tensor-core level
-int g_opt_batch_growth = 32;   // batch path: each tensor-core level covers rows [m, growth*m)
+int g_opt_batch_m0 = 128;      // batch path: rows refined exhaustively before the first tensor-core level
+int g_opt_batch_growth = 8;    // batch path: each tensor-core level covers rows [m, growth*m) (capped by k, see batch_growth)
 int g_opt_bstat = 0;           // 1: park the query group in shared memory when it fits (measured: no gain, off by default)
 int g_opt_epi2 = 2;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 2 = 8 epilogue warps, two per TMEM lane quadrant
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
@@ -278,6 +278,7 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
     ScanFn fn = pick_kernel(ix->vtype, mc, pl.direct);
     if (!fn) return fail(VSB_EINVAL, "unsupported vector type %d", ix->vtype);
     CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
 
     // the scan runs on ix->stream, the filter (+ result copy) on ix->fstream: while the filter of this query walks the
     // k-lists and compacts the candidate logs, the scan of the next query is already streaming the shard (the filter
@@ -354,6 +355,9 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         if (fast) {
             const size_t fsm = filter_fast_smem(f.S / kWarps);
             CU(cudaFuncSetAttribute((const void *)filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            // same L1/shared split as the scan kernel (max shared): kernels that want different carve-outs cannot share an SM,
+            // and the filter blocks of query i are meant to run beside the scan CTAs of query i+1
+            CU(cudaFuncSetAttribute((const void *)filter_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             filter_kernel<true><<<nblocks, fw * 32, fsm, ix->fstream>>>(f);
         } else {
             const size_t fsm = sizeof(float) * ((size_t)2 * kFilterWarps * kcap + (size_t)f.S + 32);

@@ -72,6 +72,9 @@ typedef struct {
     float *sdist;
     sqlite3_int64 *sids;
     sqlite3_int64 sn, spos;
+    /* batch mode (vector_*_scan_batch): ids/dist hold bnq x bk results, bcounts[b] valid rows of query b */
+    int batch, bnq, bk, bq, bj;
+    int *bcounts;
 } scan_cursor;
 
 /* ------------------------------------------------------------------------------------------------ helpers */
@@ -971,7 +974,7 @@ static int vt_open(sqlite3_vtab *t, sqlite3_vtab_cursor **out) {
 }
 static int vt_close(sqlite3_vtab_cursor *cur) {
     scan_cursor *c = (scan_cursor *)cur;
-    sqlite3_free(c->ids); sqlite3_free(c->dist); sqlite3_free(c->sdist); sqlite3_free(c->sids);
+    sqlite3_free(c->ids); sqlite3_free(c->dist); sqlite3_free(c->sdist); sqlite3_free(c->sids); sqlite3_free(c->bcounts);
     sqlite3_free(c);
     return SQLITE_OK;
 }
@@ -995,6 +998,31 @@ static int vt_column(sqlite3_vtab_cursor *cur, sqlite3_context *ctx, int col) { 
     return SQLITE_OK;
 }
 static int vt_rowid(sqlite3_vtab_cursor *cur, sqlite3_int64 *out) { *out = cur_id((scan_cursor *)cur); return SQLITE_OK; }
+
+/* the resident shard a scan runs on: the quantized column (staged from the shadow table on first use) or the raw column */
+static int resident_index(scan_vtab *vt, vcolumn *v, const char *tbl, const char *col, const char *fname, int quantized, vsb_index **out) {
+    if (quantized) {
+        char *name = sqlite3_mprintf("vector0_%s_%s", tbl, col);
+        int exists = name && sys_exists(vt->db, name, "table");
+        sqlite3_free(name);
+        if (!exists)
+            return vtab_error(&vt->base, "Quantization table not found for table '%s' and column '%s'. Ensure that vector_quantize() has been called before using vector_quantize_scan().", tbl, col);
+        if (!v->qix) { /* not preloaded: the reference streams the chunks from disk per query (:2186-2227); we stage them once */
+            char *err = 0;
+            if (stage_quantized(vt->db, v, &err) != SQLITE_OK) {
+                int rc = vtab_error(&vt->base, "%s: %s", fname, err ? err : "device staging failed");
+                sqlite3_free(err);
+                return rc;
+            }
+        }
+        *out = v->qix;
+        return SQLITE_OK;
+    }
+    int rc = stage_full_column(vt, v);
+    if (rc != SQLITE_OK) return rc;
+    *out = v->fix;
+    return SQLITE_OK;
+}
 
 /* common xFilter (vCursorFilterCommon, :1723-1826) */
 static int filter_common(sqlite3_vtab_cursor *cur, int argc, sqlite3_value **argv, const char *fname, int quantized, int streaming) {
@@ -1031,31 +1059,13 @@ static int filter_common(sqlite3_vtab_cursor *cur, int argc, sqlite3_value **arg
     int rc = SQLITE_OK;
     vsb_index *ix = 0;
     uint8_t *qq = 0;
+    rc = resident_index(vt, v, tbl, col, fname, quantized, &ix);
+    if (rc != SQLITE_OK) goto out;
     if (quantized) {
-        char *name = sqlite3_mprintf("vector0_%s_%s", tbl, col);
-        int exists = name && sys_exists(vt->db, name, "table");
-        sqlite3_free(name);
-        if (!exists) {
-            rc = vtab_error(&vt->base, "Quantization table not found for table '%s' and column '%s'. Ensure that vector_quantize() has been called before using vector_quantize_scan().", tbl, col);
-            goto out;
-        }
-        if (!v->qix) { /* not preloaded: the reference streams the chunks from disk per query (:2186-2227); we stage them once */
-            char *err = 0;
-            if (stage_quantized(vt->db, v, &err) != SQLITE_OK) {
-                rc = vtab_error(&vt->base, "%s: %s", fname, err ? err : "device staging failed");
-                sqlite3_free(err);
-                goto out;
-            }
-        }
-        ix = v->qix;
         qq = (uint8_t *)sqlite3_malloc(v->dim);                         /* quantize the query (:2162-2177) */
         if (!qq) { rc = SQLITE_NOMEM; goto out; }
         quantize_vec(v->vtype, query, qq, v->offset, v->scale, v->dim, v->qtype);
         query = qq;
-    } else {
-        rc = stage_full_column(vt, v);
-        if (rc != SQLITE_OK) goto out;
-        ix = v->fix;
     }
 
     if (streaming) {
@@ -1099,6 +1109,127 @@ static int vt_filter_quant(sqlite3_vtab_cursor *c, int n, const char *s, int arg
 static int vt_filter_full_stream(sqlite3_vtab_cursor *c, int n, const char *s, int argc, sqlite3_value **argv) { (void)n; (void)s; return filter_common(c, argc, argv, "vector_full_scan_stream", 0, 1); }
 static int vt_filter_quant_stream(sqlite3_vtab_cursor *c, int n, const char *s, int argc, sqlite3_value **argv) { (void)n; (void)s; return filter_common(c, argc, argv, "vector_quantize_scan_stream", 1, 1); }
 
+/* ------------------------------------------------------------------------------------------------ batched table-valued functions
+ * vector_full_scan_batch(tbl, col, vectors, k) / vector_quantize_scan_batch(tbl, col, vectors, k): B query vectors in ONE call.
+ * No counterpart in the reference (one vector per xFilter, :1774-1776); this is the SQL door to vsb_scan_topk's batch path:
+ * `vectors` is a BLOB of B x dimension elements of the column's type back to back, or a flat JSON array of B x dimension
+ * numbers.  Rows are (query, id, distance) with query = 0 .. B-1, each query's rows exactly those of the single-query function
+ * in the same order.  B >= 16 on F16/BF16/INT8/UINT8 data (not L1) is scored on the tensor cores. */
+enum { BCOL_QUERY = 4, BCOL_ID = 5, BCOL_DISTANCE = 6 };
+
+static int vt_connect_batch(sqlite3 *db, void *aux, int argc, const char *const *argv, sqlite3_vtab **out, char **err) {
+    (void)argc; (void)argv; (void)err;
+    int rc = sqlite3_declare_vtab(db, "CREATE TABLE x(tbl hidden, vector hidden, k hidden, memidx hidden, query, id, distance);");
+    if (rc != SQLITE_OK) return rc;
+    scan_vtab *vt = (scan_vtab *)sqlite3_malloc((int)sizeof *vt);
+    if (!vt) return SQLITE_NOMEM;
+    memset(vt, 0, sizeof *vt);
+    vt->db = db;
+    vt->ctx = (vcontext *)aux;
+    *out = &vt->base;
+    return SQLITE_OK;
+}
+static void batch_skip_empty(scan_cursor *c) {
+    while (c->bq < c->bnq && c->bj >= c->bcounts[c->bq]) { ++c->bq; c->bj = 0; }
+}
+static int vt_next_batch(sqlite3_vtab_cursor *cur) {
+    scan_cursor *c = (scan_cursor *)cur;
+    ++c->bj;
+    batch_skip_empty(c);
+    return SQLITE_OK;
+}
+static int vt_eof_batch(sqlite3_vtab_cursor *cur) {
+    scan_cursor *c = (scan_cursor *)cur;
+    return c->bq >= c->bnq;
+}
+static int vt_column_batch(sqlite3_vtab_cursor *cur, sqlite3_context *ctx, int col) {
+    scan_cursor *c = (scan_cursor *)cur;
+    const size_t at = (size_t)c->bq * (size_t)c->bk + (size_t)c->bj;
+    if (col == BCOL_QUERY) sqlite3_result_int(ctx, c->bq);
+    else if (col == BCOL_ID) sqlite3_result_int64(ctx, c->ids[at]);
+    else if (col == BCOL_DISTANCE) sqlite3_result_double(ctx, c->dist[at]);
+    return SQLITE_OK;
+}
+static int vt_rowid_batch(sqlite3_vtab_cursor *cur, sqlite3_int64 *out) {
+    scan_cursor *c = (scan_cursor *)cur;
+    *out = (sqlite3_int64)c->bq * (sqlite3_int64)c->bk + c->bj;     /* position in the result, unique per row */
+    return SQLITE_OK;
+}
+static int filter_batch(sqlite3_vtab_cursor *cur, int argc, sqlite3_value **argv, const char *fname, int quantized) {
+    scan_cursor *c = (scan_cursor *)cur;
+    scan_vtab *vt = (scan_vtab *)cur->pVtab;
+    c->batch = 1;
+    c->bnq = 0; c->bq = 0; c->bj = 0;
+    if (argc != 4) return vtab_error(&vt->base, "%s expects %d arguments, but %d were provided.", fname, 4, argc);
+    for (int i = 0; i < argc; ++i) {
+        int t = sqlite3_value_type(argv[i]);
+        if (i < 2 && t != SQLITE_TEXT) return vtab_error(&vt->base, "%s: argument %d must be of type TEXT (got %s).", fname, i + 1, sql_type_name(t));
+        if (i == 2 && t != SQLITE_TEXT && t != SQLITE_BLOB) return vtab_error(&vt->base, "%s: argument %d must be of type TEXT or BLOB (got %s).", fname, i + 1, sql_type_name(t));
+        if (i == 3 && t != SQLITE_INTEGER) return vtab_error(&vt->base, "%s: argument %d must be of type INTEGER (got %s).", fname, i + 1, sql_type_name(t));
+    }
+    const char *tbl = (const char *)sqlite3_value_text(argv[0]);
+    const char *col = (const char *)sqlite3_value_text(argv[1]);
+    vcolumn *v = ctx_find(vt->ctx, tbl, col);
+    if (!v) return vtab_error(&vt->base, "%s: unable to retrieve context.", fname);
+    const int need = v->dim * elem_size(v->vtype);
+    void *owned = 0;
+    const uint8_t *queries = 0;
+    int bytes = 0;
+    if (sqlite3_value_type(argv[2]) == SQLITE_TEXT) {
+        owned = json_to_blob(0, &vt->base, v->vtype, (const char *)sqlite3_value_text(argv[2]), &bytes, 0);
+        if (!owned) return SQLITE_ERROR;
+        queries = (const uint8_t *)owned;
+    } else {
+        queries = (const uint8_t *)sqlite3_value_blob(argv[2]);
+        bytes = sqlite3_value_bytes(argv[2]);
+        if (!queries) return vtab_error(&vt->base, "%s: input vectors cannot be NULL.", fname);
+    }
+    int rc = SQLITE_OK;
+    uint8_t *qq = 0;
+    vsb_index *ix = 0;
+    if (bytes <= 0 || bytes % need != 0) {
+        rc = vtab_error(&vt->base, "%s: input has %d bytes, expected a positive multiple of %d (dimension %d).", fname, bytes, need, v->dim);
+        goto out;
+    }
+    const int nq = bytes / need;
+    rc = resident_index(vt, v, tbl, col, fname, quantized, &ix);
+    if (rc != SQLITE_OK) goto out;
+    if (quantized) {                                                     /* quantize every query like vQuantRun does for one (:2162-2177) */
+        qq = (uint8_t *)sqlite3_malloc64((sqlite3_uint64)nq * (sqlite3_uint64)v->dim);
+        if (!qq) { rc = SQLITE_NOMEM; goto out; }
+        for (int b = 0; b < nq; ++b) quantize_vec(v->vtype, queries + (size_t)b * need, qq + (size_t)b * v->dim, v->offset, v->scale, v->dim, v->qtype);
+        queries = qq;
+    }
+    {
+        int k = sqlite3_value_int(argv[3]);
+        if (k == 0) { rc = SQLITE_OK; goto out; }                       /* empty result, like k = 0 of the single-query functions */
+        if (k < 0) { rc = vtab_error(&vt->base, "%s: k must not be negative.", fname); goto out; }
+        sqlite3_free(c->ids); sqlite3_free(c->dist); sqlite3_free(c->bcounts);
+        c->k_alloc = 0;
+        c->ids = (sqlite3_int64 *)sqlite3_malloc64((sqlite3_uint64)nq * (sqlite3_uint64)k * sizeof(sqlite3_int64));
+        c->dist = (double *)sqlite3_malloc64((sqlite3_uint64)nq * (sqlite3_uint64)k * sizeof(double));
+        c->bcounts = (int *)sqlite3_malloc64((sqlite3_uint64)nq * sizeof(int));
+        if (!c->ids || !c->dist || !c->bcounts) { rc = SQLITE_NOMEM; goto out; }
+        if (vsb_scan_topk(ix, v->metric, queries, nq, k, (int64_t *)c->ids, c->dist, c->bcounts, 0) != VSB_OK) {
+            rc = vtab_error(&vt->base, "%s: %s", fname, vsb_last_error());
+            goto out;
+        }
+        c->bnq = nq;
+        c->bk = k;
+        batch_skip_empty(c);
+    }
+out:
+    sqlite3_free(owned);
+    sqlite3_free(qq);
+    return rc;
+}
+static int vt_filter_full_batch(sqlite3_vtab_cursor *c, int n, const char *s, int argc, sqlite3_value **argv) { (void)n; (void)s; return filter_batch(c, argc, argv, "vector_full_scan_batch", 0); }
+static int vt_filter_quant_batch(sqlite3_vtab_cursor *c, int n, const char *s, int argc, sqlite3_value **argv) { (void)n; (void)s; return filter_batch(c, argc, argv, "vector_quantize_scan_batch", 1); }
+static sqlite3_module mod_full_batch = {0, 0, vt_connect_batch, vt_best_index, vt_disconnect, 0, vt_open, vt_close, vt_filter_full_batch, vt_next_batch,
+                                        vt_eof_batch, vt_column_batch, vt_rowid_batch, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+static sqlite3_module mod_quant_batch = {0, 0, vt_connect_batch, vt_best_index, vt_disconnect, 0, vt_open, vt_close, vt_filter_quant_batch, vt_next_batch,
+                                         vt_eof_batch, vt_column_batch, vt_rowid_batch, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
 #define SCAN_MODULE(NAME, BEST, FILTER)                                                                                      \
     static sqlite3_module NAME = {0, 0, vt_connect, BEST, vt_disconnect, 0, vt_open, vt_close, FILTER, vt_next, vt_eof, \
                                   vt_column, vt_rowid, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
@@ -1137,5 +1268,8 @@ __attribute__((visibility("default"))) int sqlite3_vector_init(sqlite3 *db, char
     if ((rc = sqlite3_create_module(db, "vector_quantize_scan", &mod_quant, ctx)) != SQLITE_OK) return rc;
     if ((rc = sqlite3_create_module(db, "vector_full_scan_stream", &mod_full_stream, ctx)) != SQLITE_OK) return rc;
     if ((rc = sqlite3_create_module(db, "vector_quantize_scan_stream", &mod_quant_stream, ctx)) != SQLITE_OK) return rc;
+    /* additions (not in the reference): batched scans */
+    if ((rc = sqlite3_create_module(db, "vector_full_scan_batch", &mod_full_batch, ctx)) != SQLITE_OK) return rc;
+    if ((rc = sqlite3_create_module(db, "vector_quantize_scan_batch", &mod_quant_batch, ctx)) != SQLITE_OK) return rc;
     return SQLITE_OK;
 }

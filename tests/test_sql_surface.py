@@ -109,3 +109,64 @@ def test_scans_through_sql_match_reference_golden():
                     assert u == v, (st, x, y)
         n_checked += 1
     assert n_checked > 40
+
+
+# ---- batched table-valued functions (an addition; the reference has one vector per call)
+def _batch_setup(n=300, dim=8, vtype="INT8"):
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(5))
+    x = rng.integers(-20, 21, (n, dim)).astype(np.int8)
+    s = ["CREATE TABLE t (id INTEGER PRIMARY KEY, e BLOB)", f"SELECT vector_init('t','e','type={vtype},dimension={dim}')"]
+    for i in range(n):
+        s.append(["INSERT INTO t(id, e) VALUES (?, ?)", [3 * i + 2, {"hex": x[i].tobytes().hex()}]])
+    return x, s
+
+
+def test_batch_tvf_argument_errors():
+    x, s = _batch_setup(5)
+    s += ["SELECT * FROM vector_full_scan_batch('t','e',x'0102030405060708')",
+          "SELECT * FROM vector_full_scan_batch('t','e',1.5,3)",
+          "SELECT * FROM vector_full_scan_batch('t','e',x'01020304',3)",
+          "SELECT * FROM vector_full_scan_batch('nope','e',x'0102030405060708',3)",
+          "SELECT * FROM vector_quantize_scan_batch('t','e','[1,2,3]',3)",
+          "SELECT * FROM vector_quantize_scan_batch('t','e',x'0102030405060708','k')",
+          "SELECT * FROM vector_quantize_scan_batch('t','e',x'0102030405060708',2)"]
+    r = run_sql(OURS, s)[-7:]
+    assert "error" in r[0]                                                    # 3 arguments: SQLite itself refuses the missing hidden column
+    assert r[1]["error"] == "vector_full_scan_batch: argument 3 must be of type TEXT or BLOB (got REAL)."
+    assert r[2]["error"] == "vector_full_scan_batch: input has 4 bytes, expected a positive multiple of 8 (dimension 8)."
+    assert r[3]["error"] == "vector_full_scan_batch: unable to retrieve context."
+    assert r[4]["error"] == "vector_quantize_scan_batch: input has 3 bytes, expected a positive multiple of 8 (dimension 8)."
+    assert r[5]["error"] == "vector_quantize_scan_batch: argument 4 must be of type INTEGER (got TEXT)."
+    assert r[6]["error"].startswith("Quantization table not found")
+
+
+@pytest.mark.gpu
+def test_batch_tvf_equals_single_query_functions():
+    import numpy as np
+    x, s = _batch_setup(300)
+    rng = np.random.Generator(np.random.PCG64(6))
+    q = rng.integers(-20, 21, (20, 8)).astype(np.int8)          # 20 queries >= 16: the batch entry point of the engine
+    allq = {"hex": q.tobytes().hex()}
+    k = 7
+    s.append(["SELECT query, id, distance FROM vector_full_scan_batch('t','e',?,?)", [allq, k]])
+    for b in range(20):
+        s.append(["SELECT id, distance FROM vector_full_scan('t','e',?,?)", [{"hex": q[b].tobytes().hex()}, k]])
+    s.append("SELECT vector_quantize('t','e')")
+    s.append(["SELECT query, id, distance FROM vector_quantize_scan_batch('t','e',?,?)", [allq, k]])
+    for b in range(20):
+        s.append(["SELECT id, distance FROM vector_quantize_scan('t','e',?,?)", [{"hex": q[b].tobytes().hex()}, k]])
+    jq = "[" + ",".join(str(int(v)) for v in q[:2].reshape(-1)) + "]"
+    s.append([f"SELECT query, id, distance FROM vector_full_scan_batch('t','e','{jq}',3)", []])
+    s.append(["SELECT count(*) FROM vector_full_scan_batch('t','e',?,0)", [allq]])
+    r = run_sql(OURS, s)
+    base = len(s) - (2 * 21 + 3)
+    for off in (base, base + 22):                                            # full scan block, then (after vector_quantize) the quantized block
+        batch = r[off]["rows"]
+        assert len(batch) == 20 * k, r[off]
+        for b in range(20):
+            single = r[off + 1 + b]["rows"]
+            assert [row[1:] for row in batch if row[0] == b] == single, (off, b)
+    js = r[-2]["rows"]
+    assert [row[2] for row in js if row[0] == 1] == [row[1] for row in r[base + 2]["rows"][:3]]     # k=3 vs the head of k=7: same distances
+    assert r[-1]["rows"] == [[0]]
