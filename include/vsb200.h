@@ -129,6 +129,15 @@ VSB_API int vsb_result_block(vsb_index *ix, int slot, void **d_block, int64_t *b
  * top-k; rows are numbered first_seq[r] + local and rowids are implicit (global row + 1).  Returns the row count. */
 VSB_API int vsb_merge_result_blocks(const void *blocks, int world, int64_t block_stride, const int64_t *first_seq, int k,
                                     int64_t *out_rowids, double *out_dist);
+/* the same for a GROUP of nq independent queries in one call (query j at queries + j * query_stride; slots first_slot ..
+ * first_slot + nq - 1): what the sharded launcher uses so that its per-query host cost stays far below one shard scan */
+VSB_API int vsb_scan_submit_group(vsb_index *ix, int metric, const void *queries, int64_t query_stride, int nq, int query_on_device,
+                                  int k, int fetch, int first_slot);
+/* vsb_merge_result_blocks for a gathered group: query j's block of shard r is at blocks + r * rank_stride + j * block_stride;
+ * results of query j at out_rowids/out_dist + j * k, out_counts[j] rows */
+VSB_API int vsb_merge_result_groups(const void *blocks, int world, int64_t rank_stride, int64_t block_stride, int nq,
+                                    const int64_t *first_seq, int k, int64_t *out_rowids, double *out_dist, int *out_counts);
+
 /* ---- batched queries on a row-sharded column (BASELINE config 4: one shard per GPU) ----------------------------
  * step 1, on every shard: the tensor-core batch path of vsb_scan_topk (same conditions: nq >= 16, f16/bf16/int8/uint8,
  * not L1) over this shard, leaving in DEVICE memory one block with, per query, the rows that entered the shard-local
@@ -151,7 +160,7 @@ VSB_API int64_t vsb_index_stat(const vsb_index *ix, const char *name);
 VSB_API void *vsb_index_stream(vsb_index *ix);           /* cudaStream_t of the engine, for event timing */
 /* kernel launch counter (all kernels launched by this library since load) */
 VSB_API int64_t vsb_kernel_launches(void);
-/* with option "time_kernels"=1 every launch is bracketed by CUDA events on the engine stream; this returns
+/* with option "time_kernels"=N (N >= 1) every N-th query's kernels are bracketed by CUDA events on their streams; this returns
  * (and resets) the summed device time and launch count of the scan kernel and of the filter kernel. */
 VSB_API int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double *filter_ms, int *filter_launches);
 /* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat","epi2","batch_debug","batch_m0","batch_growth"}; returns previous value */

@@ -44,6 +44,8 @@ _SIGNATURES = {
     "vsb_replay_topk": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "vsb_scan_device_query": (_i, [_vp, _i, _vp, _i]),
     "vsb_scan_submit": (_i, [_vp, _i, _vp, _i, _i, _i, _i]),
+    "vsb_scan_submit_group": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _i, _i]),
+    "vsb_merge_result_groups": (_i, [_vp, _i, _i64, _i64, _i, _vp, _i, _vp, _vp, _vp]),
     "vsb_collect_last": (_i, [_vp, _i, _vp, _vp, _vp]),
     "vsb_collect": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "vsb_result_block": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i64)]),
@@ -104,6 +106,15 @@ class Engine:
         if cnt < 0:
             self.check(cnt)
         return ids[:cnt], dist[:cnt]
+
+    def merge_result_groups(self, blocks: np.ndarray, world: int, rank_stride: int, block_stride: int, nq: int, first_seq: np.ndarray, k: int):
+        """merge a gathered group of nq queries in one call; returns a list of (rowids, distances)"""
+        ids = np.zeros((nq, max(k, 1)), dtype=np.int64)
+        dist = np.zeros((nq, max(k, 1)), dtype=np.float64)
+        counts = np.zeros(nq, dtype=np.int32)
+        fs = np.ascontiguousarray(first_seq, dtype=np.int64)
+        self.check(self.lib.vsb_merge_result_groups(_ptr(blocks), world, rank_stride, block_stride, nq, _ptr(fs), k, _ptr(ids), _ptr(dist), _ptr(counts)))
+        return [(ids[j, :counts[j]], dist[j, :counts[j]]) for j in range(nq)]
 
     def replay_topk(self, cands: np.ndarray, k: int, max_index: int = 0):
         cands = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
@@ -215,6 +226,12 @@ class Index:
         if slot < 0:
             self.eng.check(slot)
         return slot
+
+    def scan_submit_group(self, metric: int, queries, stride: int, nq: int, k: int, on_device: bool, first_slot: int, fetch: bool = False):
+        """nq independent queries in one call: `queries` is a device pointer (int) or a C-contiguous host array, query j at
+        byte offset j * stride; result slots first_slot .. first_slot + nq - 1"""
+        ptr = int(queries) if on_device else _ptr(queries)
+        self.eng.check(self.eng.lib.vsb_scan_submit_group(self.h, metric, ptr, stride, nq, int(on_device), k, int(fetch), first_slot))
 
     def result_block(self, slot: int):
         """(device pointer, bytes) of the slot's result block"""

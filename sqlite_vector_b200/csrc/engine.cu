@@ -42,6 +42,27 @@ int g_opt_bstat = 0;           // 1: park the query group in shared memory when 
 int g_opt_epi2 = 2;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 2 = 8 epilogue warps, two per TMEM lane quadrant
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
 
+// cudaFuncSetAttribute costs ~1 us per call; the dynamic shared memory limit of a kernel only ever needs to grow
+int set_smem_limit(const void *fn, size_t bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void *, size_t>> seen;     // per process; devices are identical B200s
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void *key = (const void *)((uintptr_t)fn ^ ((uintptr_t)dev << 56));
+    for (auto &e : seen)
+        if (e.first == key) {
+            if (e.second >= bytes) return 0;
+            cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (r == cudaSuccess) e.second = bytes;
+            return (int)r;
+        }
+    cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (r == cudaSuccess) seen.emplace_back(key, bytes);
+    return (int)r;
+}
+
 int fail(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
@@ -136,6 +157,7 @@ struct vsb_index {
     std::vector<cudaEvent_t> prof_ev;   // quadruples: before scan, after scan (scan stream), before filter, after filter (filter stream)
     std::vector<int> prof_kind;         // 1 = scan only, 2 = scan + filter
     size_t prof_used = 0;
+    unsigned prof_tick = 0;
     size_t dev_bytes = 0;
     long long st_queries = 0, st_survivors = 0, st_fallbacks = 0, st_last_survivors = 0;
     long long st_batches = 0, st_batch_cands = 0, st_batch_kept = 0, st_tc_us = 0, st_tc_rows = 0, st_batch_us = 0;
@@ -277,8 +299,9 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
     const Plan pl = make_plan(ix, kcap);
     ScanFn fn = pick_kernel(ix->vtype, mc, pl.direct);
     if (!fn) return fail(VSB_EINVAL, "unsupported vector type %d", ix->vtype);
-    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    // max-shared carve-out for the scan AND the filter kernel: kernels that want different L1/shared splits cannot share
+    // an SM, and the filter blocks of query i are meant to run beside the scan CTAs of query i+1
+    CU((cudaError_t)set_smem_limit((const void *)fn, pl.smem));
 
     // the scan runs on ix->stream, the filter (+ result copy) on ix->fstream: while the filter of this query walks the
     // k-lists and compacts the candidate logs, the scan of the next query is already streaming the shard (the filter
@@ -309,7 +332,7 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
     p.ctrl = slot ? slot->d_ctrl : nullptr;
     p.dist_all = d_dist_all;
     cudaEvent_t *pev = nullptr;
-    if (g_opt_time_kernels) {
+    if (g_opt_time_kernels > 0 && (ix->prof_tick++ % g_opt_time_kernels) == 0) {   // time_kernels = N: every N-th launch
         if (ix->prof_used + 4 > ix->prof_ev.size()) {
             for (int i = 0; i < 4; ++i) {
                 cudaEvent_t e;
@@ -354,14 +377,11 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         if (pev) CU(cudaEventRecord(pev[2], ix->fstream));
         if (fast) {
             const size_t fsm = filter_fast_smem(f.S / kWarps);
-            CU(cudaFuncSetAttribute((const void *)filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-            // same L1/shared split as the scan kernel (max shared): kernels that want different carve-outs cannot share an SM,
-            // and the filter blocks of query i are meant to run beside the scan CTAs of query i+1
-            CU(cudaFuncSetAttribute((const void *)filter_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            CU((cudaError_t)set_smem_limit((const void *)filter_kernel<true>, fsm));
             filter_kernel<true><<<nblocks, fw * 32, fsm, ix->fstream>>>(f);
         } else {
             const size_t fsm = sizeof(float) * ((size_t)2 * kFilterWarps * kcap + (size_t)f.S + 32);
-            CU(cudaFuncSetAttribute((const void *)filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            CU((cudaError_t)set_smem_limit((const void *)filter_kernel<false>, fsm));
             filter_kernel<false><<<nblocks, fw * 32, fsm, ix->fstream>>>(f);
         }
         CU(cudaGetLastError());
@@ -903,6 +923,18 @@ int vsb_scan_submit(vsb_index *ix, int metric, const void *query, int query_on_d
     return si;   // slot id (>= 0) for vsb_collect / vsb_result_block
 }
 
+int vsb_scan_submit_group(vsb_index *ix, int metric, const void *queries, int64_t query_stride, int nq, int query_on_device, int k,
+                          int fetch, int first_slot) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (nq <= 0 || first_slot < 0 || first_slot + nq > kSlots) return fail(VSB_EINVAL, "bad slot group [%d, %d)", first_slot, first_slot + nq);
+    for (int j = 0; j < nq; ++j) {
+        const int rc = vsb_scan_submit(ix, metric, (const uint8_t *)queries + (size_t)j * (size_t)query_stride, query_on_device, k, fetch,
+                                       first_slot + j);
+        if (rc < 0) return rc;
+    }
+    return VSB_OK;
+}
+
 int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k) {
     return vsb_scan_submit(ix, metric, d_query, 1, k, 1, -1);
 }
@@ -942,6 +974,18 @@ int vsb_merge_result_blocks(const void *blocks, int world, int64_t block_stride,
         }
     }
     return slots_finish(s);
+}
+
+int vsb_merge_result_groups(const void *blocks, int world, int64_t rank_stride, int64_t block_stride, int nq, const int64_t *first_seq,
+                            int k, int64_t *out_rowids, double *out_dist, int *out_counts) {
+    if (!blocks || nq <= 0 || !out_counts) return fail(VSB_EINVAL, "bad merge arguments");
+    for (int j = 0; j < nq; ++j) {
+        const int cnt = vsb_merge_result_blocks((const uint8_t *)blocks + (size_t)j * (size_t)block_stride, world, rank_stride, first_seq, k,
+                                                out_rowids + (size_t)j * k, out_dist + (size_t)j * k);
+        if (cnt < 0) return cnt;
+        out_counts[j] = cnt;
+    }
+    return VSB_OK;
 }
 
 int vsb_batch_shard_scan(vsb_index *ix, int metric, const void *queries, int nq, int k, void **d_block, int64_t *bytes) {

@@ -96,8 +96,8 @@ class DeviceExchange:
         self.next_group = 0
 
     def submit(self, metric: int, queries, k: int, on_device: bool = True):
-        """launch scan + filter for up to `group` queries (device pointers, or host arrays when on_device is False);
-        returns a ticket for finish()"""
+        """launch scan + filter for up to `group` queries (a list of device pointers, or of host arrays when on_device is
+        False); returns a ticket for finish()"""
         nq = len(queries)
         if not 0 < nq <= self.group:
             raise ValueError(f"a group holds 1..{self.group} queries")
@@ -105,6 +105,15 @@ class DeviceExchange:
         self.next_group = (gi + 1) % self.ngroups
         for j, q in enumerate(queries):
             self.ix.scan_submit(metric, q, k, on_device=on_device, fetch=False, slot=gi * self.group + j)
+        return gi, nq, self.estream.record_event(), k
+
+    def submit_strided(self, metric: int, queries, stride: int, nq: int, k: int, on_device: bool = True):
+        """the same with ONE engine call: query j at `queries` + j * stride bytes (device pointer, or a contiguous host array)"""
+        if not 0 < nq <= self.group:
+            raise ValueError(f"a group holds 1..{self.group} queries")
+        gi = self.next_group
+        self.next_group = (gi + 1) % self.ngroups
+        self.ix.scan_submit_group(metric, queries, stride, nq, k, on_device, gi * self.group)
         return gi, nq, self.estream.record_event(), k
 
     def finish(self, ticket):
@@ -122,9 +131,7 @@ class DeviceExchange:
         dist.all_gather_into_tensor(out, blk)              # rank r's blocks land at r * nq * stride
         host.copy_(out, non_blocking=True)
         cur.synchronize()
-        hn = host.numpy()
-        return [self.eng.merge_result_blocks(hn[j * self.stride:], self.world, nq * self.stride, self.first_seq, k)
-                for j in range(nq)]
+        return self.eng.merge_result_groups(host.numpy(), self.world, nq * self.stride, self.stride, nq, self.first_seq, k)
 
     def query(self, metric: int, query, k: int, on_device: bool = True):
         return self.finish(self.submit(metric, [query], k, on_device))[0]

@@ -48,8 +48,13 @@ for group in (1, 3, 8):
         results, pending = [], None
         for g0 in range(0, nq, exch.group):
             idx = range(g0, min(nq, g0 + exch.group))
-            qs = [qd[i].data_ptr() for i in idx] if on_device else [q[i] for i in idx]
-            t = exch.submit(api.L2, qs, k, on_device=on_device)
+            if group == 3:      # list form
+                qs = [qd[i].data_ptr() for i in idx] if on_device else [q[i] for i in idx]
+                t = exch.submit(api.L2, qs, k, on_device=on_device)
+            elif on_device:     # strided form: one engine call per group
+                t = exch.submit_strided(api.L2, qd[g0].data_ptr(), pitch, len(idx), k, True)
+            else:
+                t = exch.submit_strided(api.L2, q[g0:g0 + len(idx)], q.strides[0], len(idx), k, False)
             if pending is not None:
                 results += exch.finish(pending)
             pending = t
