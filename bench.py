@@ -9,7 +9,8 @@ Workload (BASELINE.json configs[1]): vector_quantize_scan, int8 quantized from a
 scanned against the whole resident corpus (3.84 GB >> 126 MB L2, so every step streams from HBM).
 
 Our arm prints `value` (queries already in HBM; launch -> candidates -> exact top-k on the host, per query) and
-`e2e` (host query in, host top-k out through the C ABI call vsb_scan_topk).  `--impl reference` times the
+`e2e` (HOST query in, host top-k out through the C ABI: vsb_scan_submit/vsb_collect with two queries in flight, the
+one-at-a-time vsb_scan_topk figure beside it; sharded runs: the grouped exchange fed with host queries).  `--impl reference` times the
 reference's own CPU scan (oracle/_ref built from the unmodified sources with -mavx2 -mfma; falls back to the
 oracle port) on all host cores.  One JSON line on stdout (rank 0).
 """
@@ -84,6 +85,16 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """the timed legs start here; keep one earlier sample (taken under the warm-up load) in case the legs are short"""
+        self.first = max(len(self.lines) - 1, 0)
+
+    def wait_first(self, timeout_s: float):
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
 
     def start(self):
         try:
@@ -103,7 +114,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -115,7 +126,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "nvidia-smi -lms 20 over the timed value leg and the timed e2e leg (plus the last sample before them)"}
 
 
 # ------------------------------------------------------------------ CPU reference arm
@@ -294,15 +306,19 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: queries resident in HBM
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()         # nvidia-smi needs a moment before its first line: start it ahead of the warm-up
     run = step_device if world == 1 else step_sharded
     for i in range(W):
         run(i)
+    if sampler:
+        sampler.wait_first(2.0)
     eng.set_option("time_kernels", 4)      # every 4th query: event records between kernels cost host time and open small gaps
     ix.profile_read()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     barrier()
+    if sampler:
+        sampler.mark()          # samples from here on (value leg and e2e leg, both under the same load) are the ones reported
     l0 = eng.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
@@ -332,7 +348,6 @@ def main():
         t = torch.tensor([ms_total], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    clocks = sampler.stop() if sampler else None
     # sequential single-query latency (launch -> complete exact top-k), for information
     lat_ms = None
     if world == 1:
@@ -349,11 +364,27 @@ def main():
     else:
         run_sharded(0, W, False)
     barrier()
+    sync_qps = None
+    if world == 1:
+        # (a) the synchronous call of the reference-facing plugin (what xFilter makes): one query at a time, each call
+        #     = pinned H2D of the query + scan + filter + D2H of the candidate block + host slot replay
+        t0s = time.perf_counter()
+        for i in range(K):
+            ix.scan_topk(api.L2, q_host[W + i], k)
+        sync_qps = K / (time.perf_counter() - t0s)
     t0 = time.perf_counter()
     surv0, q0 = ix.stat("survivors"), ix.stat("queries")
     if world == 1:
+        # (b) the asynchronous C-ABI pair vsb_scan_submit(host query) / vsb_collect with two queries in flight: the same
+        #     copies per query, but query i+1 is staged and scanning while the host finishes query i
+        pending = None
         for i in range(K):
-            ix.scan_topk(api.L2, q_host[W + i], k)
+            slot = ix.scan_submit(api.L2, q_host[W + i], k, on_device=False, fetch=True)
+            if pending is not None:
+                last_e2e = ix.collect(pending, k)
+            pending = slot
+        last_e2e = ix.collect(pending, k)
+        assert np.array_equal(last_e2e[0], last[0]) and np.array_equal(last_e2e[1], last[1]), "host-query path != device-query path"
     else:
         last_e2e = run_sharded(W, K, False)
         assert np.array_equal(last_e2e[0], last[0]) and np.array_equal(last_e2e[1], last[1]), "host-query path != device-query path"
@@ -364,6 +395,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    clocks = sampler.stop() if sampler else None
     avg_surv = (ix.stat("survivors") - surv0) / max(ix.stat("queries") - q0, 1) if world == 1 else None
     # header + block table + first 1024 candidate slots per shard, one cudaMemcpyAsync per query (group)
     d2h_bytes = int(ix.stat("fetch_bytes")) if world == 1 else int(exch.d2h_bytes_per_query)
@@ -372,11 +404,11 @@ def main():
     if world > 1 and not a.no_batched:
         try:
             B = 1024
-            shard.sharded_batch_topk(ix, api.L2, q_host[:B], k, bounds, device)          # warm-up: row norms, tensor maps
+            shard.sharded_batch_topk(ix, api.L2, q_host[:B], k, bounds, device, as_arrays=True)   # warm-up: row norms, tensor maps
             barrier()
             reps, t0b = 3, time.perf_counter()
             for _ in range(reps):
-                rb = shard.sharded_batch_topk(ix, api.L2, q_host[:B], k, bounds, device)
+                rb = shard.sharded_batch_topk(ix, api.L2, q_host[:B], k, bounds, device, as_arrays=True)
             barrier()
             dtb = (time.perf_counter() - t0b) / reps
             t = torch.tensor([dtb], device=device)
@@ -389,7 +421,7 @@ def main():
                                    "queries_per_s": B / dtb, "ms_per_batch": dtb * 1e3, "batch": B,
                                    "end_to_end_tflops": 2.0 * dim * B * n / dtb / 1e12,
                                    "path": "per shard: tcgen05 scoring + exact refine + slot replay with entry logs; NCCL all-gather of the logs; GPU merge replay",
-                                   "top1": [int(rb[0][0][0]), float(rb[0][1][0])]}
+                                   "top1": [int(rb[0][0, 0]), float(rb[1][0, 0])]}
         except Exception as ex:  # never lose the headline line
             batched_sharded = {"error": str(ex)}
     if rank != 0:
@@ -422,7 +454,9 @@ def main():
                    "exchange": None if world == 1 else f"groups of {G} independent queries: one NCCL all-gather of the shards' result blocks + one D2H per group, two groups in flight"},
         "e2e": {"value": K / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(pitch),
                 "d2h_bytes_per_step": d2h_bytes, "avg_candidates_per_query": avg_surv,
-                "note": ("vsb_scan_topk: pinned query H2D + scan/filter kernels + one D2H copy of the candidate block (header + table + 1024 slots) + host slot replay"
+                "synchronous_call_value": sync_qps,
+                "note": ("vsb_scan_submit(host query)/vsb_collect, two queries in flight: per query a pinned H2D of the query, scan/filter kernels, one D2H copy of the candidate "
+                         "block (header + table + 1024 slots), host slot replay; synchronous_call_value is the one-at-a-time vsb_scan_topk loop (the xFilter call)"
                          if world == 1 else
                          "vsb_scan_submit with HOST queries (pinned H2D per query) + scan/filter kernels on every rank + NCCL all-gather of the result blocks + D2H + host slot replay, same grouping as value")},
         "gpu_launches": int(launches),

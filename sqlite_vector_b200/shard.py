@@ -141,12 +141,13 @@ class DeviceExchange:
         return self.world * self.stride
 
 
-def sharded_batch_topk(ix, metric: int, queries: np.ndarray, k: int, bounds, device, implicit_rowids: bool = True):
+def sharded_batch_topk(ix, metric: int, queries: np.ndarray, k: int, bounds, device, implicit_rowids: bool = True, as_arrays: bool = False):
     """Batched queries over a row-sharded column (BASELINE config 4).  Every rank runs the tensor-core batch path over
     its shard (vsb_batch_shard_scan), the shards' entry-log blocks are all-gathered device-to-device (NCCL over NVLink)
     and every rank replays them in shard order on its GPU (vsb_batch_merge) — bit for bit the result of one scan over the
-    whole column.  Returns one (rowids, distances) pair per query, or None on every rank when the batch path does not
-    apply to some shard (the caller then uses the per-query exchange)."""
+    whole column.  Returns one (rowids, distances) pair per query — or, with as_arrays, (rowids[nq, k], distances[nq, k],
+    counts[nq]) without the per-query Python objects — or None on every rank when the batch path does not apply to some
+    shard (the caller then uses the per-query exchange)."""
     import torch
     import torch.distributed as dist
 
@@ -180,4 +181,6 @@ def sharded_batch_topk(ix, metric: int, queries: np.ndarray, k: int, bounds, dev
         t = torch.from_numpy(ix.lookup_rowids(seq)).to(device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ids = t.cpu().numpy()
+    if as_arrays:
+        return ids, d, counts
     return [(ids[b, :counts[b]].copy(), d[b, :counts[b]].copy()) for b in range(nq)]
