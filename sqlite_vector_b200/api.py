@@ -59,6 +59,7 @@ _SIGNATURES = {
     "vsb_kernel_launches": (_i64, []),
     "vsb_set_option": (_i, [C.c_char_p, _i]),
     "vsb_profile_read": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "vsb_debug_read": (_i, [_vp, C.c_char_p, _vp, _i64]),
 }
 
 
@@ -270,6 +271,13 @@ class Index:
 
     def stat(self, name: str) -> int:
         return int(self.eng.lib.vsb_index_stat(self.h, name.encode()))
+
+    def debug_read(self, name: str, dtype, count: int) -> np.ndarray:
+        out = np.zeros(count, dtype=dtype)
+        got = self.eng.lib.vsb_debug_read(self.h, name.encode(), _ptr(out), out.nbytes)
+        if got < 0:
+            self.eng.check(got)
+        return out[: got // out.itemsize]
 
     def profile_read(self):
         a, b = C.c_double(), C.c_double()

@@ -39,6 +39,7 @@ int g_opt_batch_debug = 0;     // 1: print per-stage timings of the batch path t
 int g_opt_batch_m0 = 128;      // batch path: rows refined exhaustively before the first tensor-core level
 int g_opt_batch_growth = 8;    // batch path: each tensor-core level covers rows [m, growth*m) (capped by k, see batch_growth)
 int g_opt_bstat = 0;           // 1: park the query group in shared memory when it fits (measured: no gain, off by default)
+int g_opt_balance = 1;         // 1: adaptive row partition of the single-query scan (per-CTA speeds feed the next partition)
 int g_opt_epi2 = 2;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 2 = 8 epilogue warps, two per TMEM lane quadrant
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
 
@@ -112,6 +113,9 @@ struct Work {
     float *d_lists = nullptr, *d_tlocal = nullptr;
     uint2 *d_logs = nullptr;
     int *d_counts = nullptr;
+    long long *d_bounds = nullptr;   // [CTAs + 1] adaptive tile partition used by the NEXT scan on this workspace
+    unsigned *d_cta_time = nullptr;  // [CTAs] cycles each scan CTA took (written by scan_kernel, read by filter_kernel)
+    long long bounds_tiles = -1;     // total tiles the bounds were laid out for (-1: not initialised)
     cudaEvent_t scanned = nullptr;   // scan stream: the scan that filled this workspace has finished
     cudaEvent_t drained = nullptr;   // filter stream: the filter that read this workspace has finished
     bool in_use = false;
@@ -276,12 +280,17 @@ int ensure_workspace(vsb_index *ix, int k) {
         if (w.d_logs) cudaFree(w.d_logs);
         if (w.d_counts) cudaFree(w.d_counts);
         if (w.d_tlocal) cudaFree(w.d_tlocal);
-        w.d_lists = nullptr; w.d_logs = nullptr; w.d_counts = nullptr; w.d_tlocal = nullptr;
+        if (w.d_bounds) cudaFree(w.d_bounds);
+        if (w.d_cta_time) cudaFree(w.d_cta_time);
+        w.d_lists = nullptr; w.d_logs = nullptr; w.d_counts = nullptr; w.d_tlocal = nullptr; w.d_bounds = nullptr; w.d_cta_time = nullptr;
+        w.bounds_tiles = -1;
         w.in_use = false;
         CU(cudaMalloc((void **)&w.d_lists, sizeof(float) * (size_t)streams * kcap));
         CU(cudaMalloc((void **)&w.d_logs, sizeof(uint2) * (size_t)streams * logcap));
         CU(cudaMalloc((void **)&w.d_counts, sizeof(int) * (size_t)streams));
         CU(cudaMalloc((void **)&w.d_tlocal, sizeof(float) * (size_t)streams));
+        CU(cudaMalloc((void **)&w.d_bounds, sizeof(long long) * (size_t)(ix->num_sms + 1)));
+        CU(cudaMalloc((void **)&w.d_cta_time, sizeof(unsigned) * (size_t)ix->num_sms));
         if (!w.scanned) CU(cudaEventCreateWithFlags(&w.scanned, cudaEventDisableTiming));
         if (!w.drained) CU(cudaEventCreateWithFlags(&w.drained, cudaEventDisableTiming));
     }
@@ -312,6 +321,17 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         ix->ws_next = (ix->ws_next + 1) % kWorks;
         if (wk->in_use) CU(cudaStreamWaitEvent(ix->stream, wk->drained, 0));   // its previous filter must have read it
     }
+    // adaptive partition (k <= 32 path only: that filter kernel maintains it): equal shares to start with
+    const long long rpw = 32 >> pl.log2P;
+    const long long total_tiles = (ix->n + rpw - 1) / rpw;
+    const bool balance = wk != nullptr && g_opt_balance && kcap == 32 && total_tiles >= 64ll * ix->num_sms;
+    if (balance && wk->bounds_tiles != total_tiles) {
+        std::vector<long long> b((size_t)ix->num_sms + 1);
+        for (int c = 0; c <= ix->num_sms; ++c) b[(size_t)c] = (total_tiles * c) / ix->num_sms;
+        CU(cudaMemcpyAsync(wk->d_bounds, b.data(), sizeof(long long) * b.size(), cudaMemcpyHostToDevice, ix->stream));   // pageable: staged before return
+        CU(cudaMemsetAsync(wk->d_cta_time, 0, sizeof(unsigned) * (size_t)ix->num_sms, ix->stream));
+        wk->bounds_tiles = total_tiles;
+    }
     ScanParams p{};
     p.vec = ix->d_vec;
     p.n = ix->n;
@@ -331,6 +351,8 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
     p.logcap = ix->ws_logcap;
     p.ctrl = slot ? slot->d_ctrl : nullptr;
     p.dist_all = d_dist_all;
+    p.bounds = balance ? wk->d_bounds : nullptr;
+    p.cta_time = balance ? wk->d_cta_time : nullptr;
     cudaEvent_t *pev = nullptr;
     if (g_opt_time_kernels > 0 && (ix->prof_tick++ % g_opt_time_kernels) == 0) {   // time_kernels = N: every N-th launch
         if (ix->prof_used + 4 > ix->prof_ev.size()) {
@@ -369,6 +391,9 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         f.hdr = slot->d_hdr;
         f.ctrl = slot->d_ctrl;
         f.seqno = ++slot->seq;
+        f.bounds = balance ? wk->d_bounds : nullptr;
+        f.cta_time = wk->d_cta_time;
+        f.total_tiles = total_tiles;
         const bool fast = (k <= 32) && filter_fast_smem(f.S / kWarps) + 2048 <= (size_t)ix->max_smem;
         const int fw = filter_warps(fast);
         const int nblocks = (f.S + fw - 1) / fw;
@@ -560,6 +585,7 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "no_batch")) p = &g_opt_no_batch;
     else if (!strcmp(name, "bstat")) p = &g_opt_bstat;
     else if (!strcmp(name, "epi2")) p = &g_opt_epi2;
+    else if (!strcmp(name, "balance")) p = &g_opt_balance;
     else if (!strcmp(name, "batch_m0")) p = &g_opt_batch_m0;
     else if (!strcmp(name, "batch_growth")) p = &g_opt_batch_growth;
     else if (!strcmp(name, "batch_debug")) p = &g_opt_batch_debug;
@@ -767,6 +793,8 @@ void vsb_index_free(vsb_index *ix) {
         if (w.d_logs) cudaFree(w.d_logs);
         if (w.d_counts) cudaFree(w.d_counts);
         if (w.d_tlocal) cudaFree(w.d_tlocal);
+        if (w.d_bounds) cudaFree(w.d_bounds);
+        if (w.d_cta_time) cudaFree(w.d_cta_time);
         if (w.scanned) cudaEventDestroy(w.scanned);
         if (w.drained) cudaEventDestroy(w.drained);
     }
@@ -870,6 +898,23 @@ int vsb_replay_topk(const vsb_candidate *cands, int n, int k, int *max_index, in
     for (int i = 0; i < n; ++i) slots_offer(s, cands[i].dist, cands[i].rowid);
     if (max_index) *max_index = s.mi;
     return slots_finish(s);
+}
+
+int vsb_debug_read(vsb_index *ix, const char *name, void *out, int64_t bytes) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (!name || !out || bytes <= 0) return fail(VSB_EINVAL, "bad debug read arguments");
+    CU(cudaSetDevice(ix->device));
+    CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaStreamSynchronize(ix->fstream));
+    const Work &w = ix->work[(ix->ws_next + kWorks - 1) % kWorks];     // the workspace of the most recent query
+    const void *src = nullptr;
+    size_t have = 0;
+    if (!strcmp(name, "cta_time")) { src = w.d_cta_time; have = sizeof(unsigned) * (size_t)ix->num_sms; }
+    else if (!strcmp(name, "bounds")) { src = w.d_bounds; have = sizeof(long long) * (size_t)(ix->num_sms + 1); }
+    else return fail(VSB_EINVAL, "unknown debug buffer %s", name);
+    if (!src) return fail(VSB_EINVAL, "no scan has run yet");
+    CU(cudaMemcpy(out, src, std::min<size_t>(have, (size_t)bytes), cudaMemcpyDeviceToHost));
+    return (int)std::min<size_t>(have, (size_t)bytes);
 }
 
 int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double *filter_ms, int *filter_launches) {

@@ -52,6 +52,12 @@ struct ScanParams {
     int logcap;
     int *ctrl;            // ctrl[1] = overflow flag
     float *dist_all;      // optional [n]
+    // adaptive row partition (optional): bounds[c] .. bounds[c+1] are the warp-tiles of CTA c (contiguous, ascending, any
+    // sizes: the exactness argument only needs streams to be contiguous row ranges in scan order).  Each CTA reports the
+    // cycles it took; filter_kernel turns speeds into the partition of the query after next (SMs do not all pull from
+    // HBM at the same rate, and with equal shares the slowest one sets the kernel time).
+    const long long *bounds;   // [gridDim.x + 1] or nullptr (equal shares)
+    unsigned *cta_time;        // [gridDim.x] or nullptr
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -389,10 +395,13 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
     const QueryNorm qn = *qn_s;
 
     // ---- this warp's stream: a contiguous range of warp-tiles (rpw rows each)
-    const long long S = (long long)gridDim.x * kWarps;
+    const long long clk0 = clock64();
     const long long sidx = (long long)blockIdx.x * kWarps + warp;
     const long long T = (prm.n + rpw - 1) / rpw;
-    const long long t0 = (T * sidx) / S, t1 = (T * (sidx + 1)) / S;
+    long long c0, c1;                                                        // this CTA's warp-tiles
+    if (prm.bounds != nullptr) { c0 = prm.bounds[blockIdx.x]; c1 = prm.bounds[blockIdx.x + 1]; }
+    else { c0 = (T * blockIdx.x) / gridDim.x; c1 = (T * (blockIdx.x + 1)) / gridDim.x; }
+    const long long t0 = c0 + ((c1 - c0) * warp) / kWarps, t1 = c0 + ((c1 - c0) * (warp + 1)) / kWarps;
     const int ntiles = (int)(t1 - t0);
 
     uint64_t *mybars = bars + warp * kMaxStages;
@@ -493,6 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
             v = warp_sort_asc(v, lane);
             mylist[lane] = v;
             __syncthreads();
+            if (tid == 0 && prm.cta_time != nullptr) prm.cta_time[blockIdx.x] = (unsigned)min((long long)0xFFFFFFFFll, clock64() - clk0);
             if (warp == 0) {
                 SortedList L;
                 L.init(lane, prm.k);
@@ -530,6 +540,10 @@ struct FilterParams {
     int *hdr;           // hdr[0] = total survivors, hdr[1] = overflow flag, hdr[2] = sequence number
     int *ctrl;          // device: [0] cursor, [1] overflow from scan_kernel, [2] blocks done
     int seqno;
+    // adaptive partition (k <= 32 path): the last block turns the scan's per-CTA cycles into new tile bounds, in place
+    long long *bounds;          // [ncta + 1] or nullptr
+    const unsigned *cta_time;   // [ncta]
+    long long total_tiles;
 };
 
 constexpr int kFilterWarps = 32;      // generic path: streams (warps) per block
@@ -709,6 +723,40 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
         const int off = wr + __popc(m & ((1u << lane) - 1u));
         if (keep && off < fp.outcap) *(off < fp.headcap ? fp.out + off : fp.out_tail + (off - fp.headcap)) = e;
         wr += __popc(m);
+    }
+    if constexpr (FAST) {
+        // ---- adaptive partition: share of CTA c for the query after next  ∝  its measured speed (tiles per cycle), damped
+        if (fp.bounds != nullptr && blockIdx.x == gridDim.x - 1 && fp.total_tiles >= 64ll * ncta && ncta <= 1024) {
+            __shared__ float spd[1024];
+            __shared__ int bad;
+            if (threadIdx.x == 0) bad = 0;
+            __syncthreads();
+            for (int c = threadIdx.x; c < ncta; c += FW * 32) {
+                const float tiles = (float)(fp.bounds[c + 1] - fp.bounds[c]);
+                const unsigned t = fp.cta_time[c];
+                if (t == 0u || !(tiles > 0.0f)) bad = 1;
+                spd[c] = tiles / (float)max(t, 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0 && !bad) {
+                double sum = 0.0;
+                for (int c = 0; c < ncta; ++c) sum += (double)spd[c];
+                double acc = 0.0;                       // running boundary in tiles
+                long long prev = 0;
+                for (int c = 0; c < ncta; ++c) {
+                    const double cur = (double)(fp.bounds[c + 1] - prev);            // old share (prev = old bounds[c])
+                    const double want = (double)fp.total_tiles * (double)spd[c] / sum;
+                    prev = fp.bounds[c + 1];
+                    acc += 0.5 * cur + 0.5 * want;
+                    long long b = (c == ncta - 1) ? fp.total_tiles : (long long)(acc + 0.5);
+                    const long long lo = fp.bounds[c] + kWarps;                       // every CTA keeps at least one tile per warp
+                    if (b < lo) b = lo;
+                    if (b > fp.total_tiles) b = fp.total_tiles;
+                    fp.bounds[c + 1] = b;
+                }
+            }
+            __syncthreads();
+        }
     }
     // last block publishes the header and re-arms the control words for the next query.  The host only reads the
     // mapped buffers after the stream has drained, so device-scope ordering between blocks is all that is needed.
