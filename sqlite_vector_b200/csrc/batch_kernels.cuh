@@ -273,21 +273,33 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
     } else if (warp >= 4) {                                                    // ===== epilogue: TMEM -> registers -> threshold test
         const int quad = warp & 3;                                             // TMEM lane quadrant this warp may read
         const int c_lo = ((warp - 4) >> 2) * (N / EPI), c_hi = c_lo + N / EPI;  // accumulator columns of this warp
+        // this thread's row norm of tile tl (raw bits; 0 for rows outside the level).  The load for tile tl+1 is issued while
+        // tile tl is tested: a global load per tile on the critical path was 7% of the epilogue's stall samples.
+        auto load_norm = [&](long long tl_) -> uint32_t {
+            if (tl_ >= ti.count) return 0u;
+            long long mt_; int ng_;
+            ti.at(tl_, mt_, ng_);
+            const long long row_ = mt_ * kTcM + quad * 32 + lane;
+            return (row_ >= prm.r0 && row_ < prm.r1) ? reinterpret_cast<const uint32_t *>(prm.norms)[row_] : 0u;
+        };
+        uint32_t nbits_next = load_norm(0);
         for (long long tl = 0; tl < ti.count; ++tl) {
             long long mt; int ng;
             ti.at(tl, mt, ng);
             const int as = (int)(tl & 1);
             const long long row = mt * kTcM + quad * 32 + lane;
             const bool rowvalid = row >= prm.r0 && row < prm.r1;
+            const uint32_t nbits = nbits_next;
+            nbits_next = load_norm(tl + 1);
             float rowf = 0.0f;
             int rowi = 0;
             if (rowvalid) {
                 if constexpr (INT8) {
-                    const int nn = reinterpret_cast<const int *>(prm.norms)[row];
+                    const int nn = (int)nbits;
                     rowi = -nn;
                     rowf = (KIND == TK_U8) ? __fsqrt_rn((float)(uint32_t)nn) : __fsqrt_rn((float)nn);
                 } else {
-                    const float nn = reinterpret_cast<const float *>(prm.norms)[row];
+                    const float nn = __uint_as_float(nbits);
                     rowf = (MC == MC_L2) ? -nn * (1.0f - 1e-4f) : __fsqrt_rn(nn);
                 }
             }

@@ -107,17 +107,22 @@ constexpr int kFirstFetch = 1024;
 constexpr size_t kResHdrBytes = 64 + sizeof(int2) * kTableCap;
 constexpr size_t kHeadBytes = kResHdrBytes + sizeof(uint2) * kFirstFetch;
 
-// scan workspace (per-stream k-lists / CTA lists, in-CTA bounds, candidate logs): written by scan_kernel, read by
-// filter_kernel.  Two of them alternate so that the filter of query i (filter stream) overlaps the scan of query i+1.
-struct Work {
+// scan workspace of ONE query (per-stream k-lists / CTA lists, in-CTA bounds, candidate logs): written by scan_kernel,
+// read by filter_kernel
+struct QWork {
     float *d_lists = nullptr, *d_tlocal = nullptr;
     uint2 *d_logs = nullptr;
     int *d_counts = nullptr;
+};
+// One launch scans up to kMaxGroup independent queries back to back (scan_kernel); a Work holds their workspaces plus what
+// is per launch.  Two Works alternate so that the filters of launch i (filter stream) overlap the scan of launch i+1.
+struct Work {
+    QWork q[kMaxGroup];
     long long *d_bounds = nullptr;   // [CTAs + 1] adaptive tile partition used by the NEXT scan on this workspace
     unsigned *d_cta_time = nullptr;  // [CTAs] cycles each scan CTA took (written by scan_kernel, read by filter_kernel)
     long long bounds_tiles = -1;     // total tiles the bounds were laid out for (-1: not initialised)
     cudaEvent_t scanned = nullptr;   // scan stream: the scan that filled this workspace has finished
-    cudaEvent_t drained = nullptr;   // filter stream: the filter that read this workspace has finished
+    cudaEvent_t drained = nullptr;   // filter stream: the filters that read this workspace have finished
     bool in_use = false;
 };
 constexpr int kWorks = 2;
@@ -160,6 +165,7 @@ struct vsb_index {
     // optional per-kernel event timing (vsb_profile_read)
     std::vector<cudaEvent_t> prof_ev;   // quadruples: before scan, after scan (scan stream), before filter, after filter (filter stream)
     std::vector<int> prof_kind;         // 1 = scan only, 2 = scan + filter
+    std::vector<int> prof_nq;           // queries scanned by the timed launch
     size_t prof_used = 0;
     unsigned prof_tick = 0;
     size_t dev_bytes = 0;
@@ -216,7 +222,7 @@ Plan make_plan(const vsb_index *ix, int kcap) {
     const int pitch = ix->pitch;
     int log2P = 0;
     while (log2P < 5 && (32 >> log2P) * (long long)pitch > g_opt_stage_bytes) ++log2P;
-    const size_t fixed = kBarrierBytes + (((size_t)pitch + (size_t)kWarps * kcap * 4 + 127) & ~(size_t)127);
+    const size_t fixed = kBarrierBytes + (((size_t)2 * pitch + (size_t)2 * kWarps * kcap * 4 + 127) & ~(size_t)127);   // 2 query + 2 list buffers
     size_t avail = (size_t)ix->max_smem > fixed ? (size_t)ix->max_smem - fixed : 0;
     if (g_opt_ring_bytes > 0 && (size_t)g_opt_ring_bytes < avail) avail = (size_t)g_opt_ring_bytes;
     const size_t wtile = (size_t)(32 >> log2P) * pitch;
@@ -276,19 +282,23 @@ int ensure_workspace(vsb_index *ix, int k) {
     ix->ws_kcap = 0;
     for (int i = 0; i < kWorks; ++i) {
         Work &w = ix->work[i];
-        if (w.d_lists) cudaFree(w.d_lists);
-        if (w.d_logs) cudaFree(w.d_logs);
-        if (w.d_counts) cudaFree(w.d_counts);
-        if (w.d_tlocal) cudaFree(w.d_tlocal);
+        for (int g = 0; g < kMaxGroup; ++g) {
+            QWork &q = w.q[g];
+            if (q.d_lists) cudaFree(q.d_lists);
+            if (q.d_logs) cudaFree(q.d_logs);
+            if (q.d_counts) cudaFree(q.d_counts);
+            if (q.d_tlocal) cudaFree(q.d_tlocal);
+            q.d_lists = nullptr; q.d_logs = nullptr; q.d_counts = nullptr; q.d_tlocal = nullptr;
+            CU(cudaMalloc((void **)&q.d_lists, sizeof(float) * (size_t)streams * kcap));
+            CU(cudaMalloc((void **)&q.d_logs, sizeof(uint2) * (size_t)streams * logcap));
+            CU(cudaMalloc((void **)&q.d_counts, sizeof(int) * (size_t)streams));
+            CU(cudaMalloc((void **)&q.d_tlocal, sizeof(float) * (size_t)streams));
+        }
         if (w.d_bounds) cudaFree(w.d_bounds);
         if (w.d_cta_time) cudaFree(w.d_cta_time);
-        w.d_lists = nullptr; w.d_logs = nullptr; w.d_counts = nullptr; w.d_tlocal = nullptr; w.d_bounds = nullptr; w.d_cta_time = nullptr;
+        w.d_bounds = nullptr; w.d_cta_time = nullptr;
         w.bounds_tiles = -1;
         w.in_use = false;
-        CU(cudaMalloc((void **)&w.d_lists, sizeof(float) * (size_t)streams * kcap));
-        CU(cudaMalloc((void **)&w.d_logs, sizeof(uint2) * (size_t)streams * logcap));
-        CU(cudaMalloc((void **)&w.d_counts, sizeof(int) * (size_t)streams));
-        CU(cudaMalloc((void **)&w.d_tlocal, sizeof(float) * (size_t)streams));
         CU(cudaMalloc((void **)&w.d_bounds, sizeof(long long) * (size_t)(ix->num_sms + 1)));
         CU(cudaMalloc((void **)&w.d_cta_time, sizeof(unsigned) * (size_t)ix->num_sms));
         if (!w.scanned) CU(cudaEventCreateWithFlags(&w.scanned, cudaEventDisableTiming));
@@ -298,28 +308,31 @@ int ensure_workspace(vsb_index *ix, int k) {
     return VSB_OK;
 }
 
-// launches scan (+ filter when k > 0) for the query in `d_query` (pitch bytes) on ix->stream
-// fetch: copy the slot's head to pinned host memory afterwards (false when the head is all-gathered on the device)
-int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *slot, float *d_dist_all, bool fetch = true) {
+// launches ONE scan kernel for nq independent queries (device pointers, pitch bytes each) on ix->stream and, when k > 0,
+// one filter launch (grid.y = nq) on ix->fstream.  slots[g] receives query g's result.
+// fetch: copy the slots' heads to pinned host memory afterwards (false when the heads are all-gathered on the device)
+int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries, int nq, int k, Slot *const *slots, float *d_dist_all,
+                      bool fetch) {
     int root = 0;
     const int mc = metric_class(metric, &root);
     if (mc < 0) return fail(VSB_EINVAL, "unknown distance metric %d", metric);
+    if (nq < 1 || nq > kMaxGroup) return fail(VSB_EINVAL, "a launch scans 1..%d queries", kMaxGroup);
     const int kcap = k > 0 ? ix->ws_kcap : 0;
     const Plan pl = make_plan(ix, kcap);
     ScanFn fn = pick_kernel(ix->vtype, mc, pl.direct);
     if (!fn) return fail(VSB_EINVAL, "unsupported vector type %d", ix->vtype);
     // max-shared carve-out for the scan AND the filter kernel: kernels that want different L1/shared splits cannot share
-    // an SM, and the filter blocks of query i are meant to run beside the scan CTAs of query i+1
+    // an SM, and the filter blocks of launch i are meant to run beside the scan CTAs of launch i+1
     CU((cudaError_t)set_smem_limit((const void *)fn, pl.smem));
 
-    // the scan runs on ix->stream, the filter (+ result copy) on ix->fstream: while the filter of this query walks the
-    // k-lists and compacts the candidate logs, the scan of the next query is already streaming the shard (the filter
+    // the scan runs on ix->stream, the filter (+ result copy) on ix->fstream: while the filters of this launch walk the
+    // k-lists and compact the candidate logs, the scan of the next launch is already streaming the shard (the filter
     // blocks are small enough to sit on the SMs beside the scan CTAs).  The two workspaces alternate.
     Work *wk = nullptr;
     if (k > 0) {
         wk = &ix->work[ix->ws_next];
         ix->ws_next = (ix->ws_next + 1) % kWorks;
-        if (wk->in_use) CU(cudaStreamWaitEvent(ix->stream, wk->drained, 0));   // its previous filter must have read it
+        if (wk->in_use) CU(cudaStreamWaitEvent(ix->stream, wk->drained, 0));   // its previous filters must have read it
     }
     // adaptive partition (k <= 32 path only: that filter kernel maintains it): equal shares to start with
     const long long rpw = 32 >> pl.log2P;
@@ -340,17 +353,21 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
     p.log2P = pl.log2P;
     p.wtile_bytes = pl.wtile_bytes;
     p.nsw = pl.nsw;
-    p.query = d_query;
     p.root = root;
     p.k = k;
     p.kcap = kcap;
-    p.lists = wk ? wk->d_lists : nullptr;
-    p.tlocal = wk ? wk->d_tlocal : nullptr;
-    p.logs = wk ? wk->d_logs : nullptr;
-    p.counts = wk ? wk->d_counts : nullptr;
     p.logcap = ix->ws_logcap;
-    p.ctrl = slot ? slot->d_ctrl : nullptr;
-    p.dist_all = d_dist_all;
+    p.nq = nq;
+    for (int g = 0; g < nq; ++g) {
+        ScanQuery &q = p.q[g];
+        q.query = d_queries[g];
+        q.lists = wk ? wk->q[g].d_lists : nullptr;
+        q.tlocal = wk ? wk->q[g].d_tlocal : nullptr;
+        q.logs = wk ? wk->q[g].d_logs : nullptr;
+        q.counts = wk ? wk->q[g].d_counts : nullptr;
+        q.ctrl = slots ? slots[g]->d_ctrl : nullptr;
+        q.dist_all = d_dist_all;
+    }
     p.bounds = balance ? wk->d_bounds : nullptr;
     p.cta_time = balance ? wk->d_cta_time : nullptr;
     cudaEvent_t *pev = nullptr;
@@ -365,6 +382,7 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         pev = &ix->prof_ev[ix->prof_used];
         ix->prof_used += 4;
         ix->prof_kind.push_back(k > 0 ? 2 : 1);
+        ix->prof_nq.push_back(nq);
         CU(cudaEventRecord(pev[0], ix->stream));
     }
     fn<<<ix->num_sms, kThreads, pl.smem, ix->stream>>>(p);
@@ -378,46 +396,62 @@ int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *
         f.S = ix->ws_streams;
         f.k = k;
         f.kcap = kcap;
-        f.lists = wk->d_lists;
-        f.tlocal = wk->d_tlocal;
-        f.logs = wk->d_logs;
-        f.counts = wk->d_counts;
         f.logcap = ix->ws_logcap;
-        f.out = slot->d_out;
         f.headcap = kFirstFetch;
-        f.out_tail = slot->d_tail;
         f.outcap = kOutCap;
-        f.table = slot->d_table;
-        f.hdr = slot->d_hdr;
-        f.ctrl = slot->d_ctrl;
-        f.seqno = ++slot->seq;
-        f.bounds = balance ? wk->d_bounds : nullptr;
-        f.cta_time = wk->d_cta_time;
-        f.total_tiles = total_tiles;
+        f.nq = nq;
         const bool fast = (k <= 32) && filter_fast_smem(f.S / kWarps) + 2048 <= (size_t)ix->max_smem;
         const int fw = filter_warps(fast);
         const int nblocks = (f.S + fw - 1) / fw;
         if (nblocks > kTableCap) return fail(VSB_ERANGE, "too many filter blocks (%d)", nblocks);
-        slot->nblocks = nblocks;
+        for (int g = 0; g < nq; ++g) {
+            FilterQuery &q = f.q[g];
+            Slot *slot = slots[g];
+            q.lists = wk->q[g].d_lists;
+            q.tlocal = wk->q[g].d_tlocal;
+            q.logs = wk->q[g].d_logs;
+            q.counts = wk->q[g].d_counts;
+            q.out = slot->d_out;
+            q.out_tail = slot->d_tail;
+            q.table = slot->d_table;
+            q.hdr = slot->d_hdr;
+            q.ctrl = slot->d_ctrl;
+            q.seqno = ++slot->seq;
+            slot->nblocks = nblocks;
+        }
+        f.bounds = balance ? wk->d_bounds : nullptr;
+        f.cta_time = wk->d_cta_time;
+        f.total_tiles = total_tiles;
         if (pev) CU(cudaEventRecord(pev[2], ix->fstream));
+        const dim3 grid((unsigned)nblocks, (unsigned)nq);
         if (fast) {
             const size_t fsm = filter_fast_smem(f.S / kWarps);
             CU((cudaError_t)set_smem_limit((const void *)filter_kernel<true>, fsm));
-            filter_kernel<true><<<nblocks, fw * 32, fsm, ix->fstream>>>(f);
+            filter_kernel<true><<<grid, fw * 32, fsm, ix->fstream>>>(f);
         } else {
             const size_t fsm = sizeof(float) * ((size_t)2 * kFilterWarps * kcap + (size_t)f.S + 32);
             CU((cudaError_t)set_smem_limit((const void *)filter_kernel<false>, fsm));
-            filter_kernel<false><<<nblocks, fw * 32, fsm, ix->fstream>>>(f);
+            filter_kernel<false><<<grid, fw * 32, fsm, ix->fstream>>>(f);
         }
         CU(cudaGetLastError());
         ++g_launches;
         if (pev) CU(cudaEventRecord(pev[3], ix->fstream));
         CU(cudaEventRecord(wk->drained, ix->fstream));
         wk->in_use = true;
-        if (fetch) CU(cudaMemcpyAsync(slot->h_res, slot->d_res, kHeadBytes, cudaMemcpyDeviceToHost, ix->fstream));
-        CU(cudaEventRecord(slot->done, ix->fstream));
+        if (fetch) {   // the heads of consecutive slots are contiguous: one copy when the group's slots are
+            bool contiguous = true;
+            for (int g = 1; g < nq; ++g) contiguous = contiguous && slots[g]->d_res == slots[g - 1]->d_res + kHeadBytes;
+            if (contiguous) CU(cudaMemcpyAsync(slots[0]->h_res, slots[0]->d_res, kHeadBytes * (size_t)nq, cudaMemcpyDeviceToHost, ix->fstream));
+            else
+                for (int g = 0; g < nq; ++g) CU(cudaMemcpyAsync(slots[g]->h_res, slots[g]->d_res, kHeadBytes, cudaMemcpyDeviceToHost, ix->fstream));
+        }
+        for (int g = 0; g < nq; ++g) CU(cudaEventRecord(slots[g]->done, ix->fstream));
     }
     return VSB_OK;
+}
+
+int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *slot, float *d_dist_all, bool fetch = true) {
+    return launch_scan_group(ix, metric, &d_query, 1, k, slot ? &slot : nullptr, d_dist_all, fetch);
 }
 
 inline int64_t rowid_of(const vsb_index *ix, uint32_t local) {
@@ -789,10 +823,12 @@ void vsb_index_free(vsb_index *ix) {
     if (ix->d_heads) cudaFree(ix->d_heads);
     for (int i = 0; i < kWorks; ++i) {
         Work &w = ix->work[i];
-        if (w.d_lists) cudaFree(w.d_lists);
-        if (w.d_logs) cudaFree(w.d_logs);
-        if (w.d_counts) cudaFree(w.d_counts);
-        if (w.d_tlocal) cudaFree(w.d_tlocal);
+        for (int g = 0; g < kMaxGroup; ++g) {
+            if (w.q[g].d_lists) cudaFree(w.q[g].d_lists);
+            if (w.q[g].d_logs) cudaFree(w.q[g].d_logs);
+            if (w.q[g].d_counts) cudaFree(w.q[g].d_counts);
+            if (w.q[g].d_tlocal) cudaFree(w.q[g].d_tlocal);
+        }
         if (w.d_bounds) cudaFree(w.d_bounds);
         if (w.d_cta_time) cudaFree(w.d_cta_time);
         if (w.scanned) cudaEventDestroy(w.scanned);
@@ -927,13 +963,14 @@ int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double 
     for (size_t i = 0; i < ix->prof_kind.size(); ++i) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ix->prof_ev[4 * i], ix->prof_ev[4 * i + 1]));
-        a += ms; ++na;
+        a += ms; na += ix->prof_nq[i];          // a launch that scans G queries counts as G scans
         if (ix->prof_kind[i] == 2) {
             CU(cudaEventElapsedTime(&ms, ix->prof_ev[4 * i + 2], ix->prof_ev[4 * i + 3]));
-            b += ms; ++nb;
+            b += ms; nb += ix->prof_nq[i];
         }
     }
     ix->prof_kind.clear();
+    ix->prof_nq.clear();
     ix->prof_used = 0;
     if (scan_ms) *scan_ms = a;
     if (scan_launches) *scan_launches = na;
@@ -971,11 +1008,33 @@ int vsb_scan_submit(vsb_index *ix, int metric, const void *query, int query_on_d
 int vsb_scan_submit_group(vsb_index *ix, int metric, const void *queries, int64_t query_stride, int nq, int query_on_device, int k,
                           int fetch, int first_slot) {
     if (check_index(ix)) return VSB_EINVAL;
+    if (!queries || k <= 0 || k > kMaxK) return fail(VSB_EINVAL, "bad scan arguments (k must be 1..%d)", kMaxK);
     if (nq <= 0 || first_slot < 0 || first_slot + nq > kSlots) return fail(VSB_EINVAL, "bad slot group [%d, %d)", first_slot, first_slot + nq);
-    for (int j = 0; j < nq; ++j) {
-        const int rc = vsb_scan_submit(ix, metric, (const uint8_t *)queries + (size_t)j * (size_t)query_stride, query_on_device, k, fetch,
-                                       first_slot + j);
-        if (rc < 0) return rc;
+    CU(cudaSetDevice(ix->device));
+    int rc = ensure_slots(ix);
+    if (rc) return rc;
+    rc = ensure_workspace(ix, k);
+    if (rc) return rc;
+    for (int g0 = 0; g0 < nq; g0 += kMaxGroup) {          // one scan launch per kMaxGroup queries
+        const int m = std::min(kMaxGroup, nq - g0);
+        const uint8_t *dq[kMaxGroup];
+        Slot *sl[kMaxGroup];
+        for (int j = 0; j < m; ++j) {
+            Slot *slot = &ix->slot[first_slot + g0 + j];
+            const uint8_t *q = (const uint8_t *)queries + (size_t)(g0 + j) * (size_t)query_stride;
+            if (!query_on_device) {
+                if (slot->seq > 0) CU(cudaEventSynchronize(slot->done));   // the slot's pinned staging buffer is free again
+                rc = stage_query(ix, slot, q);
+                if (rc) return rc;
+                q = slot->d_query;
+            }
+            dq[j] = q;
+            sl[j] = slot;
+        }
+        rc = launch_scan_group(ix, metric, dq, m, k, sl, nullptr, fetch != 0);
+        if (rc) return rc;
+        ix->last_slot = first_slot + g0 + m - 1;
+        ix->last_metric = metric;
     }
     return VSB_OK;
 }

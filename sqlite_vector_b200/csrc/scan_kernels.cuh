@@ -32,6 +32,19 @@ constexpr int kBarrierBytes = 1024;   // reserved at the start of dynamic smem f
 enum { T_F32 = 1, T_F16 = 2, T_BF16 = 3, T_U8 = 4, T_I8 = 5 };
 enum { MC_L2 = 0, MC_COS = 1, MC_DOT = 2, MC_L1 = 3 };  // L2 and SQUARED_L2 share a kernel (root flag)
 
+constexpr int kMaxGroup = 8;          // independent queries one launch can scan back to back
+
+struct ScanQuery {        // per-query pointers of a launch
+    const uint8_t *query; // device, pitch bytes, zero padded
+    float *lists;         // k <= 32: [CTAs][32] the k smallest distances of each CTA's rows, sorted ascending, +INF padded;
+                          // k > 32:  [streams][kcap] k smallest distances of each stream (unsorted)
+    float *tlocal;        // k <= 32: [streams] k-th smallest distance over the EARLIER streams of the same CTA (+INF if < k rows)
+    uint2 *logs;          // [streams][logcap] (dist bits, local row)
+    int *counts;          // [streams] log entries written (may exceed logcap => overflow)
+    int *ctrl;            // ctrl[1] = overflow flag
+    float *dist_all;      // optional [n]
+};
+
 struct ScanParams {
     const uint8_t *vec;   // [n][pitch]
     long long n;
@@ -40,18 +53,12 @@ struct ScanParams {
     int log2P;            // lanes per row = 1 << log2P
     int wtile_bytes;      // (32 >> log2P) * pitch
     int nsw;              // ring stages per warp
-    const uint8_t *query; // device, pitch bytes, zero padded
     int root;             // metric L2: take the square root
     int k;                // 0 => no top-k (dist_all only)
     int kcap;             // k rounded up to 32
-    float *lists;         // k <= 32: [CTAs][32] the k smallest distances of each CTA's rows, sorted ascending, +INF padded;
-                          // k > 32:  [streams][kcap] k smallest distances of each stream (unsorted)
-    float *tlocal;        // k <= 32: [streams] k-th smallest distance over the EARLIER streams of the same CTA (+INF if < k rows)
-    uint2 *logs;          // [streams][logcap] (dist bits, local row)
-    int *counts;          // [streams] log entries written (may exceed logcap => overflow)
     int logcap;
-    int *ctrl;            // ctrl[1] = overflow flag
-    float *dist_all;      // optional [n]
+    int nq;               // queries scanned by this launch (1..kMaxGroup)
+    ScanQuery q[kMaxGroup];
     // adaptive row partition (optional): bounds[c] .. bounds[c+1] are the warp-tiles of CTA c (contiguous, ascending, any
     // sizes: the exactness argument only needs streams to be contiguous row ranges in scan order).  Each CTA reports the
     // cycles it took; filter_kernel turns speeds into the partition of the query after next (SMs do not all pull from
@@ -342,60 +349,35 @@ struct SortedList {
 };
 
 // ------------------------------------------------------------------ the scan kernel
+// One launch scans the shard for prm.nq independent queries back to back (nq = 1: the plain single-query call; nq > 1: a
+// group submitted together by the sharded launcher).  Every CTA keeps its row range and simply starts the next query when
+// its 8 streams are done: no kernel boundary, no launch gap, and the TMA ring runs across the query boundary (the first
+// tiles of query g+1 are already in flight while the last tiles of query g are consumed).  Each query still has its own
+// k-lists, logs, counters and control words: results are exactly those of nq separate launches.
 template <int VT, int MC, bool DIRECT>
 __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);                    // [kWarps][kMaxStages]
-    QueryNorm *qn_s = reinterpret_cast<QueryNorm *>(smem + kWarps * kMaxStages * 8);
-    uint8_t *qs = smem + kBarrierBytes;                                      // query, pitch bytes
-    float *lists_s = reinterpret_cast<float *>(qs + prm.pitch);              // [kWarps][kcap]
+    uint8_t *qs = smem + kBarrierBytes;                                      // [2][pitch] query of the current / next scan
     const int list_bytes = kWarps * prm.kcap * 4;
-    uint8_t *ring = qs + ((prm.pitch + list_bytes + 127) & ~127);            // [kWarps][nsw][wtile_bytes]
+    float *lists_s = reinterpret_cast<float *>(qs + 2 * prm.pitch);          // [2][kWarps][kcap]
+    uint8_t *ring = qs + ((2 * prm.pitch + 2 * list_bytes + 127) & ~127);    // [kWarps][nsw][wtile_bytes]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P = 1 << prm.log2P, rpw = 32 >> prm.log2P;
     const int nsw = prm.nsw;
+    const long long clk0 = clock64();
 
-    // ---- prologue: barriers, query, query norm
+    // ---- prologue: barriers, first query
     if (tid == 0) {
         for (int i = 0; i < kWarps * kMaxStages; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
     for (int i = tid; i < prm.nc; i += kThreads)
-        reinterpret_cast<uint4 *>(qs)[i] = reinterpret_cast<const uint4 *>(prm.query)[i];
+        reinterpret_cast<uint4 *>(qs)[i] = reinterpret_cast<const uint4 *>(prm.q[0].query)[i];
     __syncthreads();
-    if (warp == 0) {
-        float f = 0.0f;
-        int iq = 0;
-        for (int c = lane; c < prm.nc; c += 32) {
-            const uint4 q = reinterpret_cast<const uint4 *>(qs)[c];
-            if constexpr (VT == T_U8) {
-                iq = (int)__dp4a(q.x, q.x, (uint32_t)iq); iq = (int)__dp4a(q.y, q.y, (uint32_t)iq);
-                iq = (int)__dp4a(q.z, q.z, (uint32_t)iq); iq = (int)__dp4a(q.w, q.w, (uint32_t)iq);
-            } else if constexpr (VT == T_I8) {
-                iq = __dp4a((int)q.x, (int)q.x, iq); iq = __dp4a((int)q.y, (int)q.y, iq);
-                iq = __dp4a((int)q.z, (int)q.z, iq); iq = __dp4a((int)q.w, (int)q.w, iq);
-            } else {
-                float x[8];
-                unpack8<VT>(q, x);
-                constexpr int NE = (VT == T_F32) ? 4 : 8;
-#pragma unroll
-                for (int j = 0; j < NE; ++j) f = fmaf(x[j], x[j], f);
-            }
-        }
-        for (int off = 16; off >= 1; off >>= 1) {
-            f += __shfl_xor_sync(0xFFFFFFFFu, f, off);
-            iq += __shfl_xor_sync(0xFFFFFFFFu, iq, off);
-        }
-        if (lane == 0) { qn_s->f = f; qn_s->i = iq; }
-    }
-    float *mylist = lists_s + warp * prm.kcap;
-    for (int j = lane; j < prm.kcap; j += 32) mylist[j] = (j < prm.k) ? INFINITY : -INFINITY;
-    __syncthreads();
-    const QueryNorm qn = *qn_s;
 
-    // ---- this warp's stream: a contiguous range of warp-tiles (rpw rows each)
-    const long long clk0 = clock64();
+    // ---- this warp's stream: a contiguous range of warp-tiles (rpw rows each), the same for every query of the launch
     const long long sidx = (long long)blockIdx.x * kWarps + warp;
     const long long T = (prm.n + rpw - 1) / rpw;
     long long c0, c1;                                                        // this CTA's warp-tiles
@@ -408,112 +390,165 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
     uint8_t *myring = ring + (size_t)warp * nsw * prm.wtile_bytes;
     const uint64_t pol = policy_evict_first();
 
-    auto issue = [&](int it) {  // lane 0 only
-        const long long tile = t0 + it;
-        const long long row0 = tile * rpw;
+    // The warp consumes nq * ntiles tiles in all (its stream once per query); the ring simply keeps running across query
+    // boundaries: the tile fetched into the stage just freed is always the one nsw positions ahead, which near the end of
+    // a query is one of the first tiles of the next query.
+    const unsigned total = (unsigned)prm.nq * (unsigned)ntiles;             // tiles this warp consumes in this launch
+    unsigned fetched = 0;                                                    // tiles issued so far (lane 0)
+    int pf_it = 0;                                                           // stream tile index of the next fetch
+    auto issue = [&](int s) {  // lane 0 only: next tile of the sequence into stage s
+        const long long row0 = (t0 + pf_it) * rpw;
         long long rows = prm.n - row0;
         if (rows > rpw) rows = rpw;
         const uint32_t bytes = (uint32_t)rows * (uint32_t)prm.pitch;
-        const int s = it % nsw;
         mbar_expect_tx(&mybars[s], bytes);
         bulk_g2s(myring + (size_t)s * prm.wtile_bytes, prm.vec + (size_t)row0 * prm.pitch, bytes, &mybars[s], pol);
+        ++fetched;
+        if (++pf_it == ntiles) pf_it = 0;
     };
     if constexpr (!DIRECT) {
         if (lane == 0)
-            for (int it = 0; it < nsw && it < ntiles; ++it) issue(it);
+            for (int s = 0; s < nsw && fetched < total; ++s) issue(s);
     }
+    int stage = 0;                                                           // ring position of the next tile to consume
+    uint32_t parity = 0;
 
     const int r = lane >> prm.log2P, p = lane & (P - 1);
     const int cnt = (prm.nc > p) ? (prm.nc - p + P - 1) >> prm.log2P : 0;  // chunks owned by this lane
     const int i0 = cnt ? (r % cnt) : 0;                                       // rotation: conflict-free LDS.128
-
-    float thr = INFINITY;
-    int pos = 0, logged = 0;
     const bool topk = prm.k > 0;
-    uint2 *mylog = prm.logs + (size_t)sidx * prm.logcap;
 
-    for (int it = 0; it < ntiles; ++it) {
-        const long long row0 = (t0 + it) * rpw;
-        const bool valid = (row0 + r) < prm.n;
-        Accum A = {0.f, 0.f, 0.f, 0.f, 0, 0, 0};
-        if constexpr (!DIRECT) {
-            const int s = it % nsw;
-            mbar_wait(&mybars[s], (uint32_t)((it / nsw) & 1));
-            const uint8_t *rowp = myring + (size_t)s * prm.wtile_bytes + (size_t)r * prm.pitch;
-            if (valid) {
-#pragma unroll 4
-                for (int i = 0; i < cnt; ++i) {
-                    int ii = i0 + i;
-                    if (ii >= cnt) ii -= cnt;
-                    const int c = p + (ii << prm.log2P);
-                    const uint4 rv = *reinterpret_cast<const uint4 *>(rowp + (size_t)c * 16);
-                    const uint4 qv = *reinterpret_cast<const uint4 *>(qs + (size_t)c * 16);
-                    accum16<VT, MC>(A, rv, qv);
+    for (int g = 0; g < prm.nq; ++g) {
+        const ScanQuery &Q = prm.q[g];
+        const uint8_t *qbuf = qs + (size_t)(g & 1) * prm.pitch;
+        float *mylist = lists_s + ((size_t)(g & 1) * kWarps + warp) * prm.kcap;
+
+        // query norm (every warp computes it the same way: lane-strided chunks, butterfly sum)
+        QueryNorm qn;
+        {
+            float f = 0.0f;
+            int iq = 0;
+            for (int c = lane; c < prm.nc; c += 32) {
+                const uint4 q = reinterpret_cast<const uint4 *>(qbuf)[c];
+                if constexpr (VT == T_U8) {
+                    iq = (int)__dp4a(q.x, q.x, (uint32_t)iq); iq = (int)__dp4a(q.y, q.y, (uint32_t)iq);
+                    iq = (int)__dp4a(q.z, q.z, (uint32_t)iq); iq = (int)__dp4a(q.w, q.w, (uint32_t)iq);
+                } else if constexpr (VT == T_I8) {
+                    iq = __dp4a((int)q.x, (int)q.x, iq); iq = __dp4a((int)q.y, (int)q.y, iq);
+                    iq = __dp4a((int)q.z, (int)q.z, iq); iq = __dp4a((int)q.w, (int)q.w, iq);
+                } else {
+                    float x[8];
+                    unpack8<VT>(q, x);
+                    constexpr int NE = (VT == T_F32) ? 4 : 8;
+#pragma unroll
+                    for (int j = 0; j < NE; ++j) f = fmaf(x[j], x[j], f);
                 }
             }
-            __syncwarp();
-            if (lane == 0 && it + nsw < ntiles) issue(it + nsw);
-        } else {
-            const uint8_t *rowp = prm.vec + (size_t)(row0 + r) * prm.pitch;
-            if (valid) {
-#pragma unroll 4
-                for (int i = 0; i < cnt; ++i) {
-                    const int c = p + (i << prm.log2P);
-                    const uint4 rv = ldg_stream(reinterpret_cast<const uint4 *>(rowp) + c);
-                    const uint4 qv = *reinterpret_cast<const uint4 *>(qs + (size_t)c * 16);
-                    accum16<VT, MC>(A, rv, qv);
-                }
+            for (int off = 16; off >= 1; off >>= 1) {
+                f += __shfl_xor_sync(0xFFFFFFFFu, f, off);
+                iq += __shfl_xor_sync(0xFFFFFFFFu, iq, off);
             }
+            qn.f = f; qn.i = iq;
         }
-        accum_reduce(A, P);
-        const float d = finalize<VT, MC>(A, qn, prm.root);
-        if (prm.dist_all != nullptr && valid && p == 0) prm.dist_all[row0 + r] = d;
-        if (topk) {
-            // rows are visited in scan order (lane order); strict '<' like the reference (:2102, :2145)
-            unsigned m = __ballot_sync(0xFFFFFFFFu, valid && p == 0 && d < thr);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const float dv = __shfl_sync(0xFFFFFFFFu, d, src);
-                if (dv < thr) {
-                    if (lane == 0) {
-                        if (logged < prm.logcap) mylog[logged] = make_uint2(__float_as_uint(dv), (uint32_t)(row0 + (src >> prm.log2P)));
-                        mylist[pos] = dv;
-                    }
-                    ++logged;
-                    __syncwarp();
-                    list_argmax(mylist, prm.kcap, lane, thr, pos);
-                }
-            }
-        }
-    }
-    if (topk) {
+        for (int j = lane; j < prm.kcap; j += 32) mylist[j] = (j < prm.k) ? INFINITY : -INFINITY;
         __syncwarp();
-        float *gl = prm.lists + (size_t)sidx * prm.kcap;
-        if (lane == 0) {
-            prm.counts[sidx] = logged;
-            if (logged > prm.logcap) atomicExch(&prm.ctrl[1], 1);
-        }
-        if (prm.kcap == 32) {
-            // k <= 32: the CTA's 8 streams are consecutive in scan order.  Sort each stream's list, then one warp merges
-            // them in stream order, recording the running k-th value BEFORE each stream (its in-CTA prefix bound), and
-            // publishes ONE sorted list per CTA: filter_kernel then walks 148 CTA lists instead of 1184 stream lists.
-            float v = (lane < prm.k) ? mylist[lane] : INFINITY;
-            v = warp_sort_asc(v, lane);
-            mylist[lane] = v;
-            __syncthreads();
-            if (tid == 0 && prm.cta_time != nullptr) prm.cta_time[blockIdx.x] = (unsigned)min((long long)0xFFFFFFFFll, clock64() - clk0);
-            if (warp == 0) {
-                SortedList L;
-                L.init(lane, prm.k);
-                for (int w = 0; w < kWarps; ++w) {
-                    if (lane == 0) prm.tlocal[(size_t)blockIdx.x * kWarps + w] = L.thr;
-                    L.offer_sorted(lane, lists_s[w * 32 + lane]);
+
+        float thr = INFINITY;
+        int pos = 0, logged = 0;
+        uint2 *mylog = Q.logs + (size_t)sidx * prm.logcap;
+
+        for (int it = 0; it < ntiles; ++it) {
+            const long long row0 = (t0 + it) * rpw;
+            const bool valid = (row0 + r) < prm.n;
+            Accum A = {0.f, 0.f, 0.f, 0.f, 0, 0, 0};
+            if constexpr (!DIRECT) {
+                const int s = stage;
+                mbar_wait(&mybars[s], parity);
+                if (++stage == nsw) { stage = 0; parity ^= 1u; }
+                const uint8_t *rowp = myring + (size_t)s * prm.wtile_bytes + (size_t)r * prm.pitch;
+                if (valid) {
+#pragma unroll 4
+                    for (int i = 0; i < cnt; ++i) {
+                        int ii = i0 + i;
+                        if (ii >= cnt) ii -= cnt;
+                        const int c = p + (ii << prm.log2P);
+                        const uint4 rv = *reinterpret_cast<const uint4 *>(rowp + (size_t)c * 16);
+                        const uint4 qv = *reinterpret_cast<const uint4 *>(qbuf + (size_t)c * 16);
+                        accum16<VT, MC>(A, rv, qv);
+                    }
                 }
-                prm.lists[(size_t)blockIdx.x * 32 + lane] = L.v;
+                __syncwarp();
+                if (lane == 0 && fetched < total) issue(s);                   // may already belong to the next query
+            } else {
+                const uint8_t *rowp = prm.vec + (size_t)(row0 + r) * prm.pitch;
+                if (valid) {
+#pragma unroll 4
+                    for (int i = 0; i < cnt; ++i) {
+                        const int c = p + (i << prm.log2P);
+                        const uint4 rv = ldg_stream(reinterpret_cast<const uint4 *>(rowp) + c);
+                        const uint4 qv = *reinterpret_cast<const uint4 *>(qbuf + (size_t)c * 16);
+                        accum16<VT, MC>(A, rv, qv);
+                    }
+                }
             }
-        } else {
-            for (int j = lane; j < prm.kcap; j += 32) gl[j] = mylist[j];
+            accum_reduce(A, P);
+            const float d = finalize<VT, MC>(A, qn, prm.root);
+            if (Q.dist_all != nullptr && valid && p == 0) Q.dist_all[row0 + r] = d;
+            if (topk) {
+                // rows are visited in scan order (lane order); strict '<' like the reference (:2102, :2145)
+                unsigned m = __ballot_sync(0xFFFFFFFFu, valid && p == 0 && d < thr);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float dv = __shfl_sync(0xFFFFFFFFu, d, src);
+                    if (dv < thr) {
+                        if (lane == 0) {
+                            if (logged < prm.logcap) mylog[logged] = make_uint2(__float_as_uint(dv), (uint32_t)(row0 + (src >> prm.log2P)));
+                            mylist[pos] = dv;
+                        }
+                        ++logged;
+                        __syncwarp();
+                        list_argmax(mylist, prm.kcap, lane, thr, pos);
+                    }
+                }
+            }
+        }
+        if (topk) {
+            __syncwarp();
+            if (lane == 0) {
+                Q.counts[sidx] = logged;
+                if (logged > prm.logcap) atomicExch(&Q.ctrl[1], 1);
+            }
+            if (prm.kcap == 32) {
+                // k <= 32: the CTA's 8 streams are consecutive in scan order.  Sort each stream's list, then one warp merges
+                // them in stream order, recording the running k-th value BEFORE each stream (its in-CTA prefix bound), and
+                // publishes ONE sorted list per CTA: filter_kernel then walks 148 CTA lists instead of 1184 stream lists.
+                float v = (lane < prm.k) ? mylist[lane] : INFINITY;
+                v = warp_sort_asc(v, lane);
+                mylist[lane] = v;
+            } else {
+                float *gl = Q.lists + (size_t)sidx * prm.kcap;
+                for (int j = lane; j < prm.kcap; j += 32) gl[j] = mylist[j];
+            }
+        }
+        if (g + 1 < prm.nq) {
+            // stage the next query into the other buffer: nobody reads that one any more (all warps left query g-1 at its barrier)
+            uint4 *dst = reinterpret_cast<uint4 *>(qs + (size_t)((g + 1) & 1) * prm.pitch);
+            const uint4 *src = reinterpret_cast<const uint4 *>(prm.q[g + 1].query);
+            for (int i = tid; i < prm.nc; i += kThreads) dst[i] = src[i];
+        }
+        if (g + 1 < prm.nq || (topk && prm.kcap == 32)) __syncthreads();     // query g is complete in this CTA; next query staged
+        if (g + 1 == prm.nq && tid == 0 && prm.cta_time != nullptr)
+            prm.cta_time[blockIdx.x] = (unsigned)min((long long)0xFFFFFFFFll, clock64() - clk0);
+        if (topk && prm.kcap == 32 && warp == 0) {
+            const float *ls = lists_s + (size_t)(g & 1) * kWarps * prm.kcap;
+            SortedList Lm;
+            Lm.init(lane, prm.k);
+            for (int w = 0; w < kWarps; ++w) {
+                if (lane == 0) Q.tlocal[(size_t)blockIdx.x * kWarps + w] = Lm.thr;
+                Lm.offer_sorted(lane, ls[w * 32 + lane]);
+            }
+            Q.lists[(size_t)blockIdx.x * 32 + lane] = Lm.v;
         }
     }
 }
@@ -524,22 +559,27 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
 // bound.  We use  min( k-th smallest over all streams of earlier segments,
 //                      k-th smallest over the earlier streams of the same segment ),
 // both built from the streams' final k-lists (each contains the k smallest values of its stream).
-struct FilterParams {
-    int S;              // streams
-    int k, kcap;
+struct FilterQuery {    // per-query pointers of a (group) launch: blockIdx.y selects the query
     const float *lists; // k <= 32: [S / kWarps][32] sorted CTA lists; else [S][kcap] stream lists
     const float *tlocal;// k <= 32: [S] in-CTA prefix bound of each stream (from scan_kernel)
     const uint2 *logs;  // [S][logcap]
     const int *counts;  // [S]
-    int logcap;
     uint2 *out;         // survivors (dist bits, local row), grouped by block in stream order: the first headcap of them
-    int headcap;        //   go to out (inside the slot's head, the part that travels), the rest to out_tail
-    uint2 *out_tail;
-    int outcap;         // total capacity (head + tail)
+    uint2 *out_tail;    //   go to out (inside the slot's head, the part that travels), the rest to out_tail
     int2 *table;        // [gridDim.x] (base, count) of each block's survivors in out
     int *hdr;           // hdr[0] = total survivors, hdr[1] = overflow flag, hdr[2] = sequence number
     int *ctrl;          // device: [0] cursor, [1] overflow from scan_kernel, [2] blocks done
     int seqno;
+};
+
+struct FilterParams {
+    int S;              // streams
+    int k, kcap;
+    int logcap;
+    int headcap;
+    int outcap;         // total capacity (head + tail)
+    int nq;             // queries (gridDim.y)
+    FilterQuery q[kMaxGroup];
     // adaptive partition (k <= 32 path): the last block turns the scan's per-CTA cycles into new tile bounds, in place
     long long *bounds;          // [ncta + 1] or nullptr
     const unsigned *cta_time;   // [ncta]
@@ -564,6 +604,7 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
     constexpr int FW = filter_warps(FAST);
     static_assert(FW >= kSegments, "the segment walks use the first kSegments warps");
     extern __shared__ __align__(16) uint8_t fsm[];
+    const FilterQuery &fq = fp.q[blockIdx.y];
     const int k = fp.k, kcap = fp.kcap;
     const int ncta = fp.S / kWarps;                                         // scan CTAs (FAST: each published one sorted list)
     // generic: [32][kcap] segment lists | [32][kcap] scratch | [S] in-segment prefix bound | [32] segment bounds
@@ -583,8 +624,8 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
     const int s = blockIdx.x * FW + warp;
     int n_log = 0;
     uint2 ereg[kLogRegs];
-    const uint2 *lg = fp.logs + (size_t)s * fp.logcap;
-    if (s < fp.S) n_log = min(fp.counts[s], fp.logcap);
+    const uint2 *lg = fq.logs + (size_t)s * fp.logcap;
+    if (s < fp.S) n_log = min(fq.counts[s], fp.logcap);
 #pragma unroll
     for (int i = 0; i < kLogRegs; ++i) {
         const int j = i * 32 + lane;
@@ -594,7 +635,7 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
     if constexpr (FAST) {
         const int GC = (ncta + kSegments - 1) / kSegments;                  // CTAs per segment
         {   // all CTA lists (ncta x 32 floats, ~19 KB) -> shared memory in one coalesced pass
-            const float4 *src = reinterpret_cast<const float4 *>(fp.lists);
+            const float4 *src = reinterpret_cast<const float4 *>(fq.lists);
             float4 *dst = reinterpret_cast<float4 *>(slists);
             const int tot4 = ncta * 8;
             for (int i = (int)threadIdx.x; i < tot4; i += FW * 32) dst[i] = __ldg(src + i);
@@ -629,7 +670,7 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
             const int s0 = warp * G, s1 = min(fp.S, s0 + G);
             for (int st = s0; st < s1; ++st) {
                 if (lane == 0) tlocal[st] = thr;
-                const float *src = fp.lists + (size_t)st * kcap;
+                const float *src = fq.lists + (size_t)st * kcap;
                 for (int base = 0; base < k; base += 32) {
                     const int j = base + lane;
                     const float v = (j < k) ? src[j] : INFINITY;
@@ -682,7 +723,7 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
     if (s < fp.S) {
         if constexpr (FAST) {
             const int c = s / kWarps, GC = (ncta + kSegments - 1) / kSegments;
-            T = fminf(fminf(__ldg(fp.tlocal + s), tlocal[c]), tseg[c / GC]);
+            T = fminf(fminf(__ldg(fq.tlocal + s), tlocal[c]), tseg[c / GC]);
         } else {
             T = fminf(tlocal[s], tseg[s / G]);
         }
@@ -700,9 +741,9 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
     if (threadIdx.x == 0) {
         int tot = 0;
         for (int w = 0; w < FW; ++w) { woff[w] = tot; tot += wcount[w]; }
-        const int base = atomicAdd(&fp.ctrl[0], tot);
+        const int base = atomicAdd(&fq.ctrl[0], tot);
         blk_base = base;
-        fp.table[blockIdx.x] = make_int2(base, tot);
+        fq.table[blockIdx.x] = make_int2(base, tot);
     }
     __syncthreads();
     int wr = blk_base + woff[warp];
@@ -711,7 +752,7 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
         const bool keep = __uint_as_float(ereg[i].x) < T;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
         const int off = wr + __popc(m & ((1u << lane) - 1u));
-        if (keep && off < fp.outcap) *(off < fp.headcap ? fp.out + off : fp.out_tail + (off - fp.headcap)) = ereg[i];
+        if (keep && off < fp.outcap) *(off < fp.headcap ? fq.out + off : fq.out_tail + (off - fp.headcap)) = ereg[i];
         wr += __popc(m);
     }
     for (int base = kLogRegs * 32; base < n_log; base += 32) {
@@ -721,12 +762,12 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
         if (j < n_log) { e = lg[j]; keep = __uint_as_float(e.x) < T; }
         const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
         const int off = wr + __popc(m & ((1u << lane) - 1u));
-        if (keep && off < fp.outcap) *(off < fp.headcap ? fp.out + off : fp.out_tail + (off - fp.headcap)) = e;
+        if (keep && off < fp.outcap) *(off < fp.headcap ? fq.out + off : fq.out_tail + (off - fp.headcap)) = e;
         wr += __popc(m);
     }
     if constexpr (FAST) {
         // ---- adaptive partition: share of CTA c for the query after next  ∝  its measured speed (tiles per cycle), damped
-        if (fp.bounds != nullptr && blockIdx.x == gridDim.x - 1 && fp.total_tiles >= 64ll * ncta && ncta <= 1024) {
+        if (fp.bounds != nullptr && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && fp.total_tiles >= 64ll * ncta && ncta <= 1024) {
             __shared__ float spd[1024];
             __shared__ int bad;
             if (threadIdx.x == 0) bad = 0;
@@ -763,15 +804,15 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int done = atomicAdd(&fp.ctrl[2], 1);
+        const int done = atomicAdd(&fq.ctrl[2], 1);
         if (done == (int)gridDim.x - 1) {
-            const int total = atomicAdd(&fp.ctrl[0], 0);
-            const int ovf = atomicAdd(&fp.ctrl[1], 0);
-            fp.hdr[0] = total;
-            fp.hdr[1] = (ovf != 0 || total > fp.outcap) ? 1 : 0;
-            fp.hdr[2] = fp.seqno;
-            fp.hdr[3] = (int)gridDim.x;
-            fp.ctrl[0] = 0; fp.ctrl[1] = 0; fp.ctrl[2] = 0;
+            const int total = atomicAdd(&fq.ctrl[0], 0);
+            const int ovf = atomicAdd(&fq.ctrl[1], 0);
+            fq.hdr[0] = total;
+            fq.hdr[1] = (ovf != 0 || total > fp.outcap) ? 1 : 0;
+            fq.hdr[2] = fq.seqno;
+            fq.hdr[3] = (int)gridDim.x;
+            fq.ctrl[0] = 0; fq.ctrl[1] = 0; fq.ctrl[2] = 0;
         }
     }
 }

@@ -220,3 +220,26 @@ def test_multi_shard_candidates_replay(eng, oracle):
     ids, d, _ = eng.replay_topk(cands, k)
     want_ids, want_d = oracle.scan_dense(po.L2, po.I8, q, x, rowids, k)
     assert np.array_equal(ids, want_ids) and np.array_equal(d, want_d)
+
+
+@pytest.mark.parametrize("vtype,dim,n", [(po.I8, 384, 150_000), (po.U8, 100, 40_000), (po.F32, 64, 30_000), (po.BF16, 1536, 9_000), (po.I8, 20000, 700)])
+def test_group_launch_equals_single_queries(eng, oracle, vtype, dim, n):
+    """vsb_scan_submit_group: ONE scan launch for a group of independent queries (the ring runs across query boundaries,
+    double-buffered query / k-list staging) must give exactly what the one-query-per-launch path gives, host queries and
+    device-side staging alike; the last case is the no-staging (DIRECT) kernel."""
+    import sqlite_vector_b200 as vs
+    rng = np.random.Generator(np.random.PCG64(2024 + dim))
+    x = po.convert(rng.standard_normal((n, dim), dtype=np.float32), vtype)
+    nq = 13
+    q = po.convert(rng.standard_normal((nq, dim), dtype=np.float32), vtype)
+    ix = make_index(vtype, x)
+    for metric, k in [(po.L2, 20), (po.COS, 7), (po.DOT, 32), (po.L1, 40)]:
+        want = ix.scan_topk(metric, q[0], k)            # warms the workspace for this k
+        want = [ix.scan_topk(metric, q[b], k)[0] for b in range(nq)]
+        got = []
+        for g0, m, first in [(0, 8, 0), (8, 5, 8)]:     # a full group and a partial one
+            ix.scan_submit_group(metric, np.ascontiguousarray(q[g0:g0 + m]), q.strides[0], m, k, False, first, fetch=True)
+            got += [ix.collect(first + j, k) for j in range(m)]
+        for b in range(nq):
+            assert np.array_equal(got[b][0], want[b][0]) and np.array_equal(got[b][1], want[b][1]), (vtype, metric, k, b)
+    ix.close()
