@@ -130,7 +130,9 @@ VSB_API int vsb_result_block(vsb_index *ix, int slot, void **d_block, int64_t *b
 VSB_API int vsb_merge_result_blocks(const void *blocks, int world, int64_t block_stride, const int64_t *first_seq, int k,
                                     int64_t *out_rowids, double *out_dist);
 /* the same for a GROUP of nq independent queries in one call (query j at queries + j * query_stride; slots first_slot ..
- * first_slot + nq - 1): what the sharded launcher uses so that its per-query host cost stays far below one shard scan */
+ * first_slot + nq - 1): what the sharded launcher uses so that its per-query host cost stays far below one shard scan.
+ * On small shards (one query reads < "fuse_mb" MB) up to 8 queries share ONE scan launch: every CTA starts the next
+ * query as soon as its streams are done (no launch gap, the TMA ring runs across the boundary); results are unchanged. */
 VSB_API int vsb_scan_submit_group(vsb_index *ix, int metric, const void *queries, int64_t query_stride, int nq, int query_on_device,
                                   int k, int fetch, int first_slot);
 /* vsb_merge_result_blocks for a gathered group: query j's block of shard r is at blocks + r * rank_stride + j * block_stride;
@@ -166,7 +168,7 @@ VSB_API int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches,
 /* diagnostics: copies an internal device buffer of the most recent single-query scan to `out`; name in {"cta_time" (unsigned
  * cycles per scan CTA), "bounds" (int64 tile boundaries of the adaptive row partition)}.  Returns the bytes copied or < 0. */
 VSB_API int vsb_debug_read(vsb_index *ix, const char *name, void *out, int64_t bytes);
-/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat","epi2","batch_debug","batch_m0","batch_growth","balance"}; returns previous value */
+/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat","epi2","batch_debug","batch_m0","batch_growth","balance","fuse_mb"}; returns previous value */
 VSB_API int vsb_set_option(const char *name, int value);
 
 #ifdef __cplusplus

@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
         }
         if (g + 1 < prm.nq || (topk && prm.kcap == 32)) __syncthreads();     // query g is complete in this CTA; next query staged
         if (g + 1 == prm.nq && tid == 0 && prm.cta_time != nullptr)
-            prm.cta_time[blockIdx.x] = (unsigned)min((long long)0xFFFFFFFFll, clock64() - clk0);
+            prm.cta_time[blockIdx.x] = (unsigned)min((long long)0xFFFFFFFFll, (clock64() - clk0) >> 6);   // units of 64 cycles
         if (topk && prm.kcap == 32 && warp == 0) {
             const float *ls = lists_s + (size_t)(g & 1) * kWarps * prm.kcap;
             SortedList Lm;
