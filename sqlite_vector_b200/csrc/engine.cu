@@ -39,8 +39,8 @@ int g_opt_batch_debug = 0;     // 1: print per-stage timings of the batch path t
 int g_opt_batch_m0 = 128;      // batch path: rows refined exhaustively before the first tensor-core level
 int g_opt_batch_growth = 8;    // batch path: each tensor-core level covers rows [m, growth*m) (capped by k, see batch_growth)
 int g_opt_bstat = 0;           // 1: park the query group in shared memory when it fits (measured: no gain, off by default)
-int g_opt_fuse_mb = 768;       // vsb_scan_submit_group fuses a group into one scan launch when one query's scan reads less than this
-                               // many MB (measured: +9% at 0.48 GB per query, -6% at 3.84 GB; larger shards keep one launch per query)
+int g_opt_fuse_mb = 2048;      // vsb_scan_submit_group fuses a group into one scan launch when one query's scan reads less than this
+                               // many MB (measured per query: 84.0 -> 76.9 us at 0.48 GB, 285 -> 271 us at 1.92 GB)
 int g_opt_balance = 1;         // 1: adaptive row partition of the single-query scan (per-CTA speeds feed the next partition)
 int g_opt_epi2 = 2;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 2 = 8 epilogue warps, two per TMEM lane quadrant
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)

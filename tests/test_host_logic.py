@@ -164,3 +164,35 @@ def test_merge_result_blocks_matches_oracle(oracle):
     ids, dist = eng.merge_result_blocks(blocks, world, stride, np.array(bounds[:world]), k)
     want_ids, want_d = oracle.scan_dense(po.L2, po.I8, q, x, np.arange(1, n + 1, dtype=np.int64), k)
     assert np.array_equal(ids, want_ids) and np.array_equal(dist, want_d)
+
+
+def test_merge_result_groups_matches_oracle(oracle):
+    """vsb_merge_result_groups (host): a gathered GROUP of queries, rank-major like the NCCL all-gather lays it out
+    (rank r's blocks of queries 0..G-1, then rank r+1's) == the oracle's scan of the whole column for every query"""
+    import sqlite_vector_b200 as vs
+    eng = vs.load_engine()
+    rng = np.random.Generator(np.random.PCG64(23))
+    n, dim, k, world, G = 900, 8, 20, 3, 4
+    x = rng.integers(-3, 4, (n, dim)).astype(np.int8)
+    qs = rng.integers(-3, 4, (G, dim)).astype(np.int8)
+    bounds = [0, 250, 610, n]
+    HDR, TABLE, FIRST = 64, 512 * 8, 1024
+    stride = HDR + TABLE + FIRST * 8
+    blocks = np.zeros(world * G * stride, dtype=np.uint8)
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        for j in range(G):
+            diff = x[lo:hi].astype(np.int32) - qs[j].astype(np.int32)
+            d = np.sqrt((diff * diff).sum(1).astype(np.float32))
+            blk = blocks[(r * G + j) * stride:(r * G + j + 1) * stride]
+            hdr = blk[:HDR].view(np.int32)
+            hdr[0], hdr[1], hdr[2], hdr[3] = hi - lo, 0, 1, 1
+            blk[HDR:HDR + TABLE].view(np.int32).reshape(-1, 2)[0] = (0, hi - lo)
+            out = blk[HDR + TABLE:].view(np.uint32).reshape(-1, 2)
+            out[:hi - lo, 0] = d.view(np.uint32)
+            out[:hi - lo, 1] = np.arange(hi - lo, dtype=np.uint32)
+    res = eng.merge_result_groups(blocks, world, G * stride, stride, G, np.array(bounds[:world]), k)
+    assert len(res) == G
+    for j in range(G):
+        want_ids, want_d = oracle.scan_dense(po.L2, po.I8, qs[j], x, np.arange(1, n + 1, dtype=np.int64), k)
+        assert np.array_equal(res[j][0], want_ids) and np.array_equal(res[j][1], want_d), j
