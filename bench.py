@@ -438,10 +438,11 @@ def main():
     scan_ms = prof["scan_ms"] / max(prof["scan_launches"], 1)
     shard_bytes = (hi - lo) * dim
     achieved = shard_bytes / (scan_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_scan_kernel_traffic.json")
-    if os.path.exists(tp) and world == 1 and n == 10_000_000 and dim == 384:
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    traffic = None   # dram__bytes_read + write of ONE scan launch from the newest committed `ncu --set full` capture of this workload
+    import glob
+    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "*scan_kernel_traffic.json")))
+    if tps and world == 1 and n == 10_000_000 and dim == 384:
+        traffic = json.load(open(tps[-1])).get("dram_bytes_per_launch")
 
     out = {
         "metric": METRIC_NAME, "value": K / (ms_total * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
