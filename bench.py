@@ -349,13 +349,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     # sequential single-query latency (launch -> complete exact top-k), for information
-    lat_ms = None
+    lat_ms, lat_pct = None, None
     if world == 1:
         torch.cuda.synchronize()
-        t0l = time.perf_counter()
+        lats = []
         for i in range(min(K, 100)):
+            t0l = time.perf_counter()
             step_device(W + i)
-        lat_ms = (time.perf_counter() - t0l) / min(K, 100) * 1e3
+            lats.append((time.perf_counter() - t0l) * 1e3)
+        lat_ms = float(np.mean(lats))
+        lat_pct = {"p50": float(np.percentile(lats, 50)), "p95": float(np.percentile(lats, 95)), "n": len(lats)}
 
     # ---- e2e: host query in, host top-k out, through the public C-ABI call
     if world == 1:
@@ -468,6 +471,7 @@ def main():
         "clocks": clocks,
         "wall_s_timed_region": t_wall,
         "single_query_latency_ms": lat_ms,
+        "single_query_latency_percentiles_ms": lat_pct,
         "top1": {"rowid": int(last[0][0]), "distance": float(last[1][0])},
     }
 
@@ -522,7 +526,7 @@ def batched_extras(torch, vs, api, ix, q_host, n, dim, k, device):
         B = queries.shape[0]
         index.scan_topk(metric, queries, k)                      # warm-up (row norms, tensor maps, workspaces)
         us0, rows0, bus0 = index.stat("tc_us"), index.stat("tc_rows"), index.stat("batch_us")
-        reps = 3
+        reps = 10
         for _ in range(reps):
             r = index.scan_topk(metric, queries, k)
         dt = (index.stat("batch_us") - bus0) / reps * 1e-6       # wall time inside the C-ABI call (host queries in, host top-k out)
