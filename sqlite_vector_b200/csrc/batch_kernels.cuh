@@ -177,7 +177,12 @@ struct TileIter {
 };
 
 // CH: accumulator columns per epilogue step (64 = two 32-column TMEM loads in flight per buffer, 32 = one)
-template <int KIND, int MC, bool BSTAT, int EPI, int CH>
+// TEST: 0 = every score is compared with its query's bound (IADD3 + predicate-chained ISETP per score);
+//       1 = EXPERIMENTAL, not yet run on a GPU (option "epi_max", off by default): integer kinds, L2 / DOT, CH = 32: a running
+//           maximum of (2 s_j - qc_j) resp. (s_j - qc_j) over the 32 columns and ONE comparison against the row constant
+//           (a hit exists in the chunk iff the maximum passes); the exact per-column masks are only computed for chunks
+//           that have a hit, as before.
+template <int KIND, int MC, bool BSTAT, int EPI, int CH, int TEST = 0>
 __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, const TcParams prm) {
     constexpr bool INT8 = (KIND == TK_I8 || KIND == TK_U8);
@@ -208,7 +213,15 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
-    for (int i = threadIdx.x; i < prm.NG * N; i += tc_threads(EPI)) qc_s[i] = __float_as_uint(prm.qc[i]);
+    constexpr bool kMaxTest = (TEST == 1) && INT8 && (MC == MC_L2 || MC == MC_DOT) && CH == 32;
+    for (int i = threadIdx.x; i < prm.NG * N; i += tc_threads(EPI)) {
+        uint32_t c = __float_as_uint(prm.qc[i]);
+        if constexpr (kMaxTest) {
+            // keep (2 s - qc) inside int32: bounds beyond +-2^30 mean "always" / "never" for every reachable score anyway
+            c = (uint32_t)max(-(1 << 30), min(1 << 30, (int)c));
+        }
+        qc_s[i] = c;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -321,11 +334,31 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
                 const uint4 *qc4 = reinterpret_cast<const uint4 *>(qc_s + ng * N + cb);
                 constexpr int C0 = CH < 32 ? CH : 32;                          // columns in the first 32-column half
                 bool any0 = false, any1 = false;
+                if constexpr (kMaxTest) {
+                    int m0 = INT_MIN, m1 = INT_MIN;
 #pragma unroll
-                for (int j4 = 0; j4 < C0 / 4; ++j4) {
-                    const uint4 c = qc4[j4];
-                    any0 |= tc_hit<INT8, MC>(v[4 * j4 + 0], c.x, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 1], c.y, rowf, rowi) |
-                            tc_hit<INT8, MC>(v[4 * j4 + 2], c.z, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 3], c.w, rowf, rowi);
+                    for (int j4 = 0; j4 < C0 / 4; ++j4) {
+                        const uint4 c = qc4[j4];
+                        int a, b, e, f;
+                        if constexpr (MC == MC_L2) {
+                            a = 2 * (int)v[4 * j4 + 0] - (int)c.x; b = 2 * (int)v[4 * j4 + 1] - (int)c.y;
+                            e = 2 * (int)v[4 * j4 + 2] - (int)c.z; f = 2 * (int)v[4 * j4 + 3] - (int)c.w;
+                        } else {
+                            a = (int)v[4 * j4 + 0] - (int)c.x; b = (int)v[4 * j4 + 1] - (int)c.y;
+                            e = (int)v[4 * j4 + 2] - (int)c.z; f = (int)v[4 * j4 + 3] - (int)c.w;
+                        }
+                        m0 = max(m0, max(a, b));
+                        m1 = max(m1, max(e, f));
+                    }
+                    const int m = max(m0, m1);
+                    any0 = (MC == MC_L2) ? (m >= -rowi) : (m > 0);          // rowi = -|row|^2:  2 s + rowi >= qc  <=>  2 s - qc >= -rowi
+                } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < C0 / 4; ++j4) {
+                        const uint4 c = qc4[j4];
+                        any0 |= tc_hit<INT8, MC>(v[4 * j4 + 0], c.x, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 1], c.y, rowf, rowi) |
+                                tc_hit<INT8, MC>(v[4 * j4 + 2], c.z, rowf, rowi) | tc_hit<INT8, MC>(v[4 * j4 + 3], c.w, rowf, rowi);
+                    }
                 }
                 if constexpr (CH == 64) {
                     if (two) {
