@@ -182,7 +182,9 @@ struct TileIter {
 //           maximum of (2 s_j - qc_j) resp. (s_j - qc_j) over the 32 columns and ONE comparison against the row constant
 //           (a hit exists in the chunk iff the maximum passes); the exact per-column masks are only computed for chunks
 //           that have a hit, as before.
-template <int KIND, int MC, bool BSTAT, int EPI, int CH, int TEST = 0>
+// NACC: accumulator buffers in TMEM (NACC * N <= 512 columns).  2 is the validated configuration; 4 (with N = 128) is
+//       EXPERIMENTAL like TEST = 1 (option "tc_n" = 128): the MMA may run three tiles ahead of the epilogue.
+template <int KIND, int MC, bool BSTAT, int EPI, int CH, int TEST = 0, int NACC = 2>
 __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, const TcParams prm) {
     constexpr bool INT8 = (KIND == TK_I8 || KIND == TK_U8);
@@ -195,19 +197,19 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
     uint8_t *tail = bsm + (BSTAT ? (size_t)prm.KB * b_bytes : 0);
     uint64_t *full = reinterpret_cast<uint64_t *>(tail);
     uint64_t *empty = full + kTcMaxStages;
-    uint64_t *tfull = empty + kTcMaxStages;                                    // [2] accumulator ready
-    uint64_t *tempty = tfull + 2;                                              // [2] accumulator drained
-    uint64_t *bfull = tempty + 2;                                              // BSTAT: query group landed / no longer read
+    uint64_t *tfull = empty + kTcMaxStages;                                    // [NACC] accumulator ready
+    uint64_t *tempty = tfull + NACC;                                           // [NACC] accumulator drained
+    uint64_t *bfull = tempty + NACC;                                           // BSTAT: query group landed / no longer read
     uint64_t *bempty = bfull + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bempty + 1);
     uint32_t *qc_s = tmem_slot + 4;                                            // [NG*N]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tmem_cols = (2 * N <= 32) ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
+    const uint32_t tmem_cols = (NACC * N <= 32) ? 32 : (NACC * N <= 64 ? 64 : (NACC * N <= 128 ? 128 : (NACC * N <= 256 ? 256 : 512)));
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTcMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * EPI); }
+        for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * EPI); }
         mbar_init(bfull, 1);
         mbar_init(bempty, 1);
         fence_barrier_init();
@@ -259,11 +261,11 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
             const uint32_t idesc = umma_idesc(KIND, N);
             int it = 0;
             for (long long tl = 0; tl < ti.count; ++tl) {
-                const int as = (int)(tl & 1);
+                const int as = (int)(tl % NACC);
                 if constexpr (BSTAT) {
                     if (tl % ti.per_cta == 0) mbar_wait(bfull, (uint32_t)((tl / ti.per_cta) & 1));
                 }
-                mbar_wait(&tempty[as], (uint32_t)(((tl >> 1) & 1) ^ 1));
+                mbar_wait(&tempty[as], (uint32_t)(((tl / NACC) & 1) ^ 1));
                 tc_fence_after();
                 for (int kb = 0; kb < prm.KB; ++kb, ++it) {
                     const int s = it % NS;
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
         for (long long tl = 0; tl < ti.count; ++tl) {
             long long mt; int ng;
             ti.at(tl, mt, ng);
-            const int as = (int)(tl & 1);
+            const int as = (int)(tl % NACC);
             const long long row = mt * kTcM + quad * 32 + lane;
             const bool rowvalid = row >= prm.r0 && row < prm.r1;
             const uint32_t nbits = nbits_next;
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
                     rowf = (MC == MC_L2) ? -nn * (1.0f - 1e-4f) : __fsqrt_rn(nn);
                 }
             }
-            mbar_wait(&tfull[as], (uint32_t)((tl >> 1) & 1));
+            mbar_wait(&tfull[as], (uint32_t)((tl / NACC) & 1));
             tc_fence_after();
             // 64 accumulator columns per step, software pipelined: the TMEM loads of step i+1 are in flight while step i
             // is tested (TMEM reads are 64 B/clk/SM: 128x256 fp32 accumulators take >= 2048 clk to drain, which bounds

@@ -42,6 +42,7 @@ int g_opt_bstat = 0;           // 1: park the query group in shared memory when 
 int g_opt_fuse_mb = 2048;      // vsb_scan_submit_group fuses a group into one scan launch when one query's scan reads less than this
                                // many MB (measured per query: 84.0 -> 76.9 us at 0.48 GB, 285 -> 271 us at 1.92 GB)
 int g_opt_balance = 1;         // 1: adaptive row partition of the single-query scan (per-CTA speeds feed the next partition)
+int g_opt_tc_n = 0;            // 128: EXPERIMENTAL 128-query tensor-core tiles with four TMEM accumulator buffers (not validated on a GPU yet)
 int g_opt_epi_max = 0;         // 1: EXPERIMENTAL running-maximum pre-test in the int8/uint8 L2 / DOT tensor-core epilogue (not validated on a GPU yet)
 int g_opt_epi2 = 2;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 2 = 8 epilogue warps, two per TMEM lane quadrant
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
@@ -623,6 +624,7 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "bstat")) p = &g_opt_bstat;
     else if (!strcmp(name, "epi2")) p = &g_opt_epi2;
     else if (!strcmp(name, "epi_max")) p = &g_opt_epi_max;
+    else if (!strcmp(name, "tc_n")) p = &g_opt_tc_n;
     else if (!strcmp(name, "balance")) p = &g_opt_balance;
     else if (!strcmp(name, "fuse_mb")) p = &g_opt_fuse_mb;
     else if (!strcmp(name, "batch_m0")) p = &g_opt_batch_m0;
