@@ -12,3 +12,5 @@ timeout 300 python tools/quick_batch.py --n 4000000 --dim 384 --vtype 4 --metric
 timeout 300 python tools/quick_batch.py --n 4000000 --dim 768 --vtype 3 --metric 4 --nq 1024 --iters 2 --sweep "tc_n=128" 2>&1 | tail -3
 echo "== fused group launches on a full shard (was slower than single launches before the cta_time fix: re-measure)"
 timeout 200 python tools/quick_group.py --n 10000000 --queries 160 2>&1 | tail -4
+echo "== SQL end to end (SURVEY 8d: true SQL path at n <= 1M), ours vs the reference AVX2 build"
+timeout 600 python tools/sql_bench.py --n 1000000 --dim 384 --queries 50 --which both 2>&1 | cut -c1-700
