@@ -467,7 +467,10 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "vsb::scan_kernel<int8,L2>", "avg_launch_ms": scan_ms, "launches_timed": prof["scan_launches"],
                      "filter_kernel_avg_ms": prof["filter_ms"] / max(prof["filter_launches"], 1), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": int(shard_bytes)},
+                     "algorithmic_bytes_per_launch": int(shard_bytes),
+                     "note": "peak is the measured COPY bandwidth (reads + writes); this kernel only reads, so frac can exceed 1.0 "
+                             "(ncu: dram__bytes_read = 1.0001 x algorithmic bytes per launch, profiles/r01e_ncu_summary.json); "
+                             "avg_launch_ms is per query scan (a fused launch of G queries counts as G scans)"},
         "clocks": clocks,
         "wall_s_timed_region": t_wall,
         "single_query_latency_ms": lat_ms,
