@@ -131,8 +131,9 @@ VSB_API int vsb_merge_result_blocks(const void *blocks, int world, int64_t block
                                     int64_t *out_rowids, double *out_dist);
 /* the same for a GROUP of nq independent queries in one call (query j at queries + j * query_stride; slots first_slot ..
  * first_slot + nq - 1): what the sharded launcher uses so that its per-query host cost stays far below one shard scan.
- * On small shards (one query reads < "fuse_mb" MB) up to 8 queries share ONE scan launch: every CTA starts the next
- * query as soon as its streams are done (no launch gap, the TMA ring runs across the boundary); results are unchanged. */
+ * With option "fuse_mb" > 0 (off by default) and one query reading fewer MB than that, up to 8 queries share ONE scan
+ * launch: every CTA starts the next query as soon as its streams are done (no launch gap, the TMA ring runs across the
+ * boundary); results are unchanged. */
 VSB_API int vsb_scan_submit_group(vsb_index *ix, int metric, const void *queries, int64_t query_stride, int nq, int query_on_device,
                                   int k, int fetch, int first_slot);
 /* vsb_merge_result_blocks for a gathered group: query j's block of shard r is at blocks + r * rank_stride + j * block_stride;

@@ -39,8 +39,10 @@ int g_opt_batch_debug = 0;     // 1: print per-stage timings of the batch path t
 int g_opt_batch_m0 = 128;      // batch path: rows refined exhaustively before the first tensor-core level
 int g_opt_batch_growth = 8;    // batch path: each tensor-core level covers rows [m, growth*m) (capped by k, see batch_growth)
 int g_opt_bstat = 0;           // 1: park the query group in shared memory when it fits (measured: no gain, off by default)
-int g_opt_fuse_mb = 2048;      // vsb_scan_submit_group fuses a group into one scan launch when one query's scan reads less than this
-                               // many MB (measured per query: 84.0 -> 76.9 us at 0.48 GB, 285 -> 271 us at 1.92 GB)
+int g_opt_fuse_mb = 0;         // > 0: vsb_scan_submit_group fuses a group into ONE scan launch when one query's scan reads less than this
+                               // many MB (measured per query on one GPU: 84.0 -> 76.9 us at 0.48 GB; 2 GPUs: 285 -> 271 us at 1.92 GB).
+                               // Off by default: a persistent 8-query launch leaves the NCCL all-gather of the previous group no SM until
+                               // it ends (2 GPUs: the step-vs-scan gap grew from 3 to 14 us per query), not yet measured at 8 GPUs.
 int g_opt_balance = 1;         // 1: adaptive row partition of the single-query scan (per-CTA speeds feed the next partition)
 int g_opt_tc_n = 0;            // 128: EXPERIMENTAL 128-query tensor-core tiles with four TMEM accumulator buffers (not validated on a GPU yet)
 int g_opt_epi_max = 0;         // 1: EXPERIMENTAL running-maximum pre-test in the int8/uint8 L2 / DOT tensor-core epilogue (not validated on a GPU yet)

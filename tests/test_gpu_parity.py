@@ -233,7 +233,7 @@ def test_group_launch_equals_single_queries(eng, oracle, vtype, dim, n):
     nq = 13
     q = po.convert(rng.standard_normal((nq, dim), dtype=np.float32), vtype)
     ix = make_index(vtype, x)
-    assert n * dim * x.itemsize < (768 << 20)           # small shard: the group IS fused into one launch per 8 queries
+    old_fuse = eng.set_option("fuse_mb", 4096)          # the option is off by default: here the group IS fused (8 queries per launch)
     for metric, k in [(po.L2, 20), (po.COS, 7), (po.DOT, 32), (po.L1, 40)]:
         want = ix.scan_topk(metric, q[0], k)            # warms the workspace for this k
         want = [ix.scan_topk(metric, q[b], k)[0] for b in range(nq)]
@@ -243,4 +243,5 @@ def test_group_launch_equals_single_queries(eng, oracle, vtype, dim, n):
             got += [ix.collect(first + j, k) for j in range(m)]
         for b in range(nq):
             assert np.array_equal(got[b][0], want[b][0]) and np.array_equal(got[b][1], want[b][1]), (vtype, metric, k, b)
+    eng.set_option("fuse_mb", old_fuse)
     ix.close()
