@@ -252,8 +252,24 @@ Plan make_plan(const vsb_index *ix, int kcap) {
     return pl;
 }
 
-int ensure_slots(vsb_index *ix) {
-    if (ix->slots_ready) return VSB_OK;
+void free_slots(vsb_index *ix) {
+    for (int i = 0; i < kSlots; ++i) {
+        Slot &s = ix->slot[i];
+        if (s.h_tail) cudaFreeHost(s.h_tail);
+        if (s.d_tail) cudaFree(s.d_tail);
+        if (s.h_query) cudaFreeHost(s.h_query);
+        if (s.d_query) cudaFree(s.d_query);
+        if (s.d_ctrl) cudaFree(s.d_ctrl);
+        if (s.done) cudaEventDestroy(s.done);
+        s = Slot();
+    }
+    if (ix->h_heads) cudaFreeHost(ix->h_heads);
+    if (ix->d_heads) cudaFree(ix->d_heads);
+    ix->h_heads = nullptr; ix->d_heads = nullptr;
+    ix->slots_ready = false;
+}
+
+int ensure_slots_alloc(vsb_index *ix) {
     CU(cudaMalloc((void **)&ix->d_heads, kHeadBytes * kSlots));
     CU(cudaMemset(ix->d_heads, 0, kHeadBytes * kSlots));
     CU(cudaHostAlloc((void **)&ix->h_heads, kHeadBytes * kSlots, cudaHostAllocDefault));
@@ -274,6 +290,13 @@ int ensure_slots(vsb_index *ix) {
         CU(cudaMemset(s.d_ctrl, 0, sizeof(int) * 4));
         CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
+    return VSB_OK;
+}
+
+int ensure_slots(vsb_index *ix) {
+    if (ix->slots_ready) return VSB_OK;
+    const int rc = ensure_slots_alloc(ix);
+    if (rc != VSB_OK) { free_slots(ix); return rc; }   // a half-built slot set must not be reused (g_err keeps the CUDA message)
     ix->slots_ready = true;
     return VSB_OK;
 }
@@ -323,7 +346,10 @@ int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries
     const int mc = metric_class(metric, &root);
     if (mc < 0) return fail(VSB_EINVAL, "unknown distance metric %d", metric);
     if (nq < 1 || nq > kMaxGroup) return fail(VSB_EINVAL, "a launch scans 1..%d queries", kMaxGroup);
-    const int kcap = k > 0 ? ix->ws_kcap : 0;
+    // per-launch list stride: the workspace may have been sized by an earlier, larger k (ensure_workspace never shrinks), but
+    // the scan's list layout, the filter's FAST/generic choice and its shared-memory layout all follow THIS query's k
+    const int kcap = k > 0 ? ((k + 31) & ~31) : 0;
+    if (kcap > ix->ws_kcap) return fail(VSB_EINVAL, "scan workspace too small for k = %d", k);
     const Plan pl = make_plan(ix, kcap);
     ScanFn fn = pick_kernel(ix->vtype, mc, pl.direct);
     if (!fn) return fail(VSB_EINVAL, "unsupported vector type %d", ix->vtype);
@@ -406,7 +432,7 @@ int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries
         f.headcap = kFirstFetch;
         f.outcap = kOutCap;
         f.nq = nq;
-        const bool fast = (k <= 32) && filter_fast_smem(f.S / kWarps) + 2048 <= (size_t)ix->max_smem;
+        const bool fast = (kcap == 32) && filter_fast_smem(f.S / kWarps) + 2048 <= (size_t)ix->max_smem;
         const int fw = filter_warps(fast);
         const int nblocks = (f.S + fw - 1) / fw;
         if (nblocks > kTableCap) return fail(VSB_ERANGE, "too many filter blocks (%d)", nblocks);
@@ -633,6 +659,7 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "batch_growth")) p = &g_opt_batch_growth;
     else if (!strcmp(name, "batch_debug")) p = &g_opt_batch_debug;
     if (!p) return fail(VSB_EINVAL, "unknown option %s", name);
+    if (value < 0) return fail(VSB_EINVAL, "option %s: values are non-negative", name);   // so that a negative return is always an error
     int old = *p;
     *p = value;
     return old;
@@ -708,6 +735,7 @@ static int append_rows(vsb_index *ix, const uint8_t *src, size_t src_stride, siz
         for (long long i = 0; i < ix->n; ++i) ix->h_rowids[(size_t)i] = ix->first_seq + i + 1;
         ix->implicit_ids = false;
     }
+    if (pitch > kStageBuf) return fail(VSB_ERANGE, "row pitch %zu exceeds the %zu-byte staging buffer", pitch, (size_t)kStageBuf);
     const int64_t per_buf = (int64_t)(kStageBuf / pitch);
     int64_t done = 0;
     while (done < nrows) {
@@ -819,17 +847,7 @@ void vsb_index_free(vsb_index *ix) {
         if (ix->stage[b]) cudaFreeHost(ix->stage[b]);
         if (ix->stage_ev[b]) cudaEventDestroy(ix->stage_ev[b]);
     }
-    for (int i = 0; i < kSlots; ++i) {
-        Slot &s = ix->slot[i];
-        if (s.h_tail) cudaFreeHost(s.h_tail);
-        if (s.d_tail) cudaFree(s.d_tail);
-        if (s.h_query) cudaFreeHost(s.h_query);
-        if (s.d_query) cudaFree(s.d_query);
-        if (s.d_ctrl) cudaFree(s.d_ctrl);
-        if (s.done) cudaEventDestroy(s.done);
-    }
-    if (ix->h_heads) cudaFreeHost(ix->h_heads);
-    if (ix->d_heads) cudaFree(ix->d_heads);
+    free_slots(ix);
     for (int i = 0; i < kWorks; ++i) {
         Work &w = ix->work[i];
         for (int g = 0; g < kMaxGroup; ++g) {

@@ -116,9 +116,8 @@ __device__ __forceinline__ uint32_t fkey(float f) {
 // ------------------------------------------------------------------ accumulation
 struct Accum {
     float s0, s1;   // fp: primary sum split in two chains (dot / sum of squares / sum of |d|)
-    float ny, nx;   // fp cosine: row norm, query norm (f16 only; others take the query norm once per CTA)
+    float ny;       // fp cosine: row norm (the query norm is computed once per query, QueryNorm)
     int ia, ib;     // int: dot or sad, row norm
-    int flag;       // f16 cosine: an infinity was seen
 };
 
 template <int VT>
@@ -169,30 +168,23 @@ __device__ __forceinline__ void accum16(Accum &A, const uint4 r, const uint4 q) 
         float y[8], x[8];
         unpack8<VT>(r, y);
         unpack8<VT>(q, x);
+        // Plain IEEE accumulation, no per-element special-value tests: the reference's NaN-lane / infinity policies (f16: all
+        // metrics, src/distance-cpu.c:318-466; bf16 L2: :164-197) only matter for rows (or queries) that actually hold a NaN or
+        // an infinity, and any such element leaves a non-finite accumulator behind.  Those rows are recomputed with the
+        // reference's exact policy by special_row_distance (row_needs_exact below).
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
             float &s = (j & 1) ? A.s1 : A.s0;
-            // NaN-lane policies of the reference: f16 kernels skip a lane when either INPUT is NaN
-            // (src/distance-cpu.c:338, 383, 413, 444); the bf16 L2 kernel skips a NaN DIFFERENCE (:182).
-            bool skip = false;
-            if constexpr (VT == T_F16) skip = (x[j] != x[j]) || (y[j] != y[j]);
             if constexpr (MC == MC_L2) {
-                float d = x[j] - y[j];
-                if constexpr (VT == T_BF16) skip = (d != d);
-                if (!skip) s = fmaf(d, d, s);
+                const float d = x[j] - y[j];
+                s = fmaf(d, d, s);
             } else if constexpr (MC == MC_L1) {
-                if (!skip) s += fabsf(x[j] - y[j]);
+                s += fabsf(x[j] - y[j]);
             } else if constexpr (MC == MC_DOT) {
-                if (!skip) s = fmaf(x[j], y[j], s);
+                s = fmaf(x[j], y[j], s);
             } else {  // cosine
-                if (!skip) {
-                    s = fmaf(x[j], y[j], s);
-                    A.ny = fmaf(y[j], y[j], A.ny);
-                    if constexpr (VT == T_F16) {
-                        A.nx = fmaf(x[j], x[j], A.nx);
-                        A.flag |= (isinf(x[j]) || isinf(y[j])) ? 1 : 0;
-                    }
-                }
+                s = fmaf(x[j], y[j], s);
+                A.ny = fmaf(y[j], y[j], A.ny);
             }
         }
     }
@@ -237,9 +229,10 @@ __device__ __forceinline__ float finalize(const Accum &A, const QueryNorm qn, in
         else if constexpr (MC == MC_L1) d = s;
         else {
             if constexpr (VT == T_F16) {
-                // src/distance-cpu.c:444-465: any Inf -> 1; bad denominator -> 1; clamp cos to [-1,1]
-                float den = __fmul_rn(__fsqrt_rn(A.nx), __fsqrt_rn(A.ny));
-                if (A.flag || !(den > 0.0f) || isinf(den) || den != den || isinf(s) || s != s) d = 1.0f;
+                // src/distance-cpu.c:457-465 (finite inputs; rows with NaN / Inf go through special_row_distance): bad
+                // denominator -> 1; clamp cos to [-1,1]
+                float den = __fmul_rn(__fsqrt_rn(qn.f), __fsqrt_rn(A.ny));
+                if (!(den > 0.0f) || isinf(den) || den != den || isinf(s) || s != s) d = 1.0f;
                 else {
                     float c = __fdiv_rn(s, den);
                     c = fminf(1.0f, fmaxf(-1.0f, c));
@@ -256,15 +249,90 @@ __device__ __forceinline__ float finalize(const Accum &A, const QueryNorm qn, in
     return (fabsf(d) <= 8.0f * FLT_EPSILON) ? 0.0f : d;
 }
 
+// ------------------------------------------------------------------ rows with NaN / Inf elements (rare path)
+// kinds whose reference kernel treats special values differently from IEEE propagation
+template <int VT, int MC>
+__host__ __device__ constexpr bool has_special_policy() { return VT == T_F16 || (VT == T_BF16 && MC == MC_L2); }
+
+// after accum_reduce: does this row (or the query) hold a NaN / Inf?  (finite inputs cannot overflow these sums: f16 values
+// are <= 65504 and bf16 L2 sums of finite differences stay finite up to ~1e19 per element)
+template <int VT, int MC>
+__device__ __forceinline__ bool row_needs_exact(const Accum &A, const QueryNorm qn) {
+    if constexpr (!has_special_policy<VT, MC>()) return false;
+    else if constexpr (MC == MC_COS) return !(fabsf(A.s0 + A.s1) <= FLT_MAX) || !(A.ny <= FLT_MAX) || !(qn.f <= FLT_MAX);
+    else return !(fabsf(A.s0 + A.s1) <= FLT_MAX);
+}
+
+// The reference's own element loop for one row, one thread, element order (fp32 accumulation instead of double: the result
+// classes — NaN, +Inf, -Inf, 1.0 — are exact, finite values agree to ~dim * 2^-24):
+//   f16 L2 / L1 (:318-400): a lane with an infinity that is not paired with an equal-signed infinity -> +INF at once (checked
+//       BEFORE the NaN test); NaN lanes skipped; Inf - Inf poisons the sum (LASSQ: NaN unless every other difference is 0)
+//   f16 DOT (:402-432): NaN lanes skipped; the FIRST infinite product decides: -INF if positive, +INF if negative; Inf * 0 poisons
+//   f16 COSINE (:434-466): NaN lanes skipped; any infinity -> 1; bad denominator / non-finite dot -> 1; clamp to [-1, 1]
+//   bf16 L2 (:164-197): float difference; infinite difference -> +INF; NaN difference skipped
+template <int VT, int MC>
+__device__ __noinline__ float special_row_distance(const uint8_t *row, const uint8_t *query, int nelem, int root) {
+    const uint16_t *yb = reinterpret_cast<const uint16_t *>(row), *xb = reinterpret_cast<const uint16_t *>(query);
+    float s = 0.0f, nx = 0.0f, ny = 0.0f;
+    bool poisoned = false, anynz = false;
+    for (int e = 0; e < nelem; ++e) {
+        float xf, yf;
+        if constexpr (VT == T_F16) {
+            xf = __half2float(__ushort_as_half(xb[e]));
+            yf = __half2float(__ushort_as_half(yb[e]));
+        } else {
+            xf = __uint_as_float((uint32_t)xb[e] << 16);
+            yf = __uint_as_float((uint32_t)yb[e] << 16);
+        }
+        if constexpr (VT == T_BF16) {                                           // bf16 L2
+            const float d = xf - yf;
+            if (isinf(d)) return INFINITY;
+            if (d == d) s = fmaf(d, d, s);
+        } else if constexpr (MC == MC_L2 || MC == MC_L1) {
+            const bool xi = isinf(xf), yi = isinf(yf);
+            if ((xi || yi) && !(xi && yi && (xf > 0.0f) == (yf > 0.0f))) return INFINITY;
+            if (xf != xf || yf != yf) continue;
+            const float d = xf - yf;                                            // NaN for an equal-signed pair of infinities
+            if (d != d) poisoned = true;
+            else {
+                if (d != 0.0f) anynz = true;
+                s = (MC == MC_L2) ? fmaf(d, d, s) : s + fabsf(d);
+            }
+        } else {
+            if (xf != xf || yf != yf) continue;
+            if constexpr (MC == MC_DOT) {
+                const float p = xf * yf;                                        // exact for f16 inputs; infinite iff an input is
+                if (isinf(p)) return p > 0.0f ? -INFINITY : INFINITY;
+                s += p;                                                         // Inf * 0 = NaN poisons, like `dot += p`
+            } else {
+                if (isinf(xf) || isinf(yf)) return 1.0f;
+                s = fmaf(xf, yf, s); nx = fmaf(xf, xf, nx); ny = fmaf(yf, yf, ny);
+            }
+        }
+    }
+    float d;
+    if constexpr (MC == MC_L2) {
+        if (poisoned) d = anynz ? __int_as_float(0x7FC00000) : 0.0f;           // LASSQ: scale == 0 -> 0 (:346 / :194)
+        else d = root ? __fsqrt_rn(s) : s;
+    } else if constexpr (MC == MC_L1) {
+        d = poisoned ? __int_as_float(0x7FC00000) : s;
+    } else if constexpr (MC == MC_DOT) {
+        d = -s;
+    } else {
+        const float den = __fmul_rn(__fsqrt_rn(nx), __fsqrt_rn(ny));
+        if (!(den > 0.0f) || isinf(den) || den != den || isinf(s) || s != s) d = 1.0f;
+        else d = 1.0f - fminf(1.0f, fmaxf(-1.0f, __fdiv_rn(s, den)));
+    }
+    return (fabsf(d) <= 8.0f * FLT_EPSILON) ? 0.0f : d;
+}
+
 __device__ __forceinline__ void accum_reduce(Accum &A, int P) {
     for (int off = P >> 1; off >= 1; off >>= 1) {
         A.s0 += __shfl_xor_sync(0xFFFFFFFFu, A.s0, off);
         A.s1 += __shfl_xor_sync(0xFFFFFFFFu, A.s1, off);
         A.ny += __shfl_xor_sync(0xFFFFFFFFu, A.ny, off);
-        A.nx += __shfl_xor_sync(0xFFFFFFFFu, A.nx, off);
         A.ia += __shfl_xor_sync(0xFFFFFFFFu, A.ia, off);
         A.ib += __shfl_xor_sync(0xFFFFFFFFu, A.ib, off);
-        A.flag |= __shfl_xor_sync(0xFFFFFFFFu, A.flag, off);
     }
 }
 
@@ -417,6 +485,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
     const int cnt = (prm.nc > p) ? (prm.nc - p + P - 1) >> prm.log2P : 0;  // chunks owned by this lane
     const int i0 = cnt ? (r % cnt) : 0;                                       // rotation: conflict-free LDS.128
     const bool topk = prm.k > 0;
+    constexpr bool kFix16 = has_special_policy<VT, MC>();   // rows with NaN / Inf are recomputed from the staged tile: see special_row_distance
+    const uint8_t *fix_row = nullptr;
+    int fix_stage = 0;
 
     for (int g = 0; g < prm.nq; ++g) {
         const ScanQuery &Q = prm.q[g];
@@ -460,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
         for (int it = 0; it < ntiles; ++it) {
             const long long row0 = (t0 + it) * rpw;
             const bool valid = (row0 + r) < prm.n;
-            Accum A = {0.f, 0.f, 0.f, 0.f, 0, 0, 0};
+            Accum A = {0.f, 0.f, 0.f, 0, 0};
             if constexpr (!DIRECT) {
                 const int s = stage;
                 mbar_wait(&mybars[s], parity);
@@ -478,7 +549,12 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
                     }
                 }
                 __syncwarp();
-                if (lane == 0 && fetched < total) issue(s);                   // may already belong to the next query
+                if constexpr (!kFix16) {
+                    if (lane == 0 && fetched < total) issue(s);               // may already belong to the next query
+                } else {
+                    fix_row = rowp;                                           // the stage stays valid until the fix-up below has run
+                    fix_stage = s;
+                }
             } else {
                 const uint8_t *rowp = prm.vec + (size_t)(row0 + r) * prm.pitch;
                 if (valid) {
@@ -492,7 +568,17 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanParams prm)
                 }
             }
             accum_reduce(A, P);
-            const float d = finalize<VT, MC>(A, qn, prm.root);
+            float d = finalize<VT, MC>(A, qn, prm.root);
+            if constexpr (kFix16) {
+                if (valid && p == 0 && row_needs_exact<VT, MC>(A, qn)) {
+                    if constexpr (DIRECT) fix_row = prm.vec + (size_t)(row0 + r) * prm.pitch;
+                    d = special_row_distance<VT, MC>(fix_row, qbuf, prm.pitch / 2, prm.root);
+                }
+                if constexpr (!DIRECT) {
+                    __syncwarp();
+                    if (lane == 0 && fetched < total) issue(fix_stage);
+                }
+            }
             if (Q.dist_all != nullptr && valid && p == 0) Q.dist_all[row0 + r] = d;
             if (topk) {
                 // rows are visited in scan order (lane order); strict '<' like the reference (:2102, :2145)

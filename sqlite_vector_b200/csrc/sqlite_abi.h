@@ -112,7 +112,7 @@ enum {
     VSQ_bind_blob = 2, VSQ_bind_double = 3, VSQ_bind_int = 4, VSQ_bind_int64 = 5, VSQ_bind_text = 10,
     VSQ_column_blob = 19, VSQ_column_bytes = 20, VSQ_column_double = 27, VSQ_column_int = 28, VSQ_column_int64 = 29,
     VSQ_column_text = 36, VSQ_column_type = 38, VSQ_create_function = 45, VSQ_create_module = 47, VSQ_declare_vtab = 50,
-    VSQ_errmsg = 53, VSQ_exec = 55, VSQ_finalize = 57, VSQ_free = 58, VSQ_malloc = 68, VSQ_mprintf = 69, VSQ_reset = 77,
+    VSQ_errmsg = 53, VSQ_exec = 55, VSQ_finalize = 57, VSQ_free = 58, VSQ_get_autocommit = 60, VSQ_malloc = 68, VSQ_mprintf = 69, VSQ_reset = 77,
     VSQ_result_blob = 78, VSQ_result_double = 79, VSQ_result_error = 80, VSQ_result_int = 82, VSQ_result_int64 = 83,
     VSQ_result_null = 84, VSQ_result_text = 85, VSQ_result_value = 89, VSQ_step = 94, VSQ_total_changes = 97,
     VSQ_user_data = 101, VSQ_value_blob = 102, VSQ_value_bytes = 103, VSQ_value_double = 105, VSQ_value_int = 106,
@@ -152,6 +152,7 @@ extern const sqlite3_api_routines *vsq_api;
 #define sqlite3_exec VSQ_CALL(exec, int (*)(sqlite3 *, const char *, int (*)(void *, int, char **, char **), void *, char **))
 #define sqlite3_finalize VSQ_CALL(finalize, int (*)(sqlite3_stmt *))
 #define sqlite3_free VSQ_CALL(free, void (*)(void *))
+#define sqlite3_get_autocommit VSQ_CALL(get_autocommit, int (*)(sqlite3 *))
 #define sqlite3_malloc VSQ_CALL(malloc, void *(*)(int))
 #define sqlite3_malloc64 VSQ_CALL(malloc64, void *(*)(sqlite3_uint64))
 #define sqlite3_mprintf VSQ_CALL(mprintf, char *(*)(const char *, ...))

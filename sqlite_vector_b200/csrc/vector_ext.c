@@ -45,9 +45,13 @@ typedef struct {
     float scale, offset;           /* quantization parameters (persisted in _sqliteai_vector) */
     vsb_index *qix;                /* resident quantized shard */
     int q_user_preloaded;          /* vector_quantize_preload was called (vs. staged lazily by a scan) */
+    int q_tainted;                 /* lazily staged inside an open transaction: never reused (a ROLLBACK moves no counter) */
+    sqlite3_int64 q_dataver;       /* PRAGMA data_version when the lazily staged copy was last verified */
+    sqlite3_int64 q_fp[4];         /* shadow-table fingerprint at stage time: COUNT(*), SUM(counter), MIN(rowid1), MAX(rowid2) */
     vsb_index *fix;                /* resident raw column for vector_full_scan */
     sqlite3_int64 fix_dataver;
     int fix_changes;
+    int fix_tainted;               /* staged inside an open transaction: never reused */
 } vcolumn;
 
 typedef struct {
@@ -717,9 +721,23 @@ done:
     return rc;
 }
 
+/* what identifies the shadow table's current contents cheaply (vector_quantize rewrites every chunk) */
+static void quant_fingerprint(sqlite3 *db, const vcolumn *v, sqlite3_int64 fp[4]) {
+    fp[0] = fp[1] = fp[2] = fp[3] = -1;
+    char *sql = sqlite3_mprintf("SELECT COUNT(*), SUM(counter), MIN(rowid1), MAX(rowid2) FROM vector0_%q_%q;", v->tbl, v->col);
+    sqlite3_stmt *st = 0;
+    if (sql && sqlite3_prepare_v2(db, sql, -1, &st, 0) == SQLITE_OK && sqlite3_step(st) == SQLITE_ROW)
+        for (int i = 0; i < 4; ++i) fp[i] = sqlite3_column_int64(st, i);
+    sqlite3_finalize(st);
+    sqlite3_free(sql);
+}
+
 /* stage every shadow-table chunk into HBM (the GPU counterpart of the loop at :1382-1394) */
 static int stage_quantized(sqlite3 *db, vcolumn *v, char **errmsg) {
     if (v->qix) { vsb_index_free(v->qix); v->qix = 0; }
+    v->q_tainted = !sqlite3_get_autocommit(db);
+    v->q_dataver = query_int64(db, "PRAGMA data_version;");
+    quant_fingerprint(db, v, v->q_fp);
     char *sql = sqlite3_mprintf("SELECT SUM(counter) FROM vector0_%q_%q;", v->tbl, v->col);
     sqlite3_int64 rows = sql ? query_int64(db, sql) : 0;
     sqlite3_free(sql);
@@ -785,8 +803,10 @@ static int do_quantize(sqlite3_context *ctx, const char *tbl, const char *col, c
     sqlite3 *db = sqlite3_context_db_handle(ctx);
     uint32_t counter = 0;
     char *sql = 0;
-    int rc = sqlite3_exec(db, "BEGIN;", 0, 0, 0);
-    if (rc != SQLITE_OK) goto fail;
+    /* The reference brackets the rebuild with a bare BEGIN/COMMIT (:1418, :1446), which fails inside a caller's transaction
+     * and then ROLLBACKs the caller's work.  A savepoint nests: deviation 9 in DESIGN.md. */
+    int rc = sqlite3_exec(db, "SAVEPOINT vsb_quantize;", 0, 0, 0);
+    if (rc != SQLITE_OK) { sqlite3_result_error_code(ctx, rc); return rc; }
     sql = sqlite3_mprintf("DROP TABLE IF EXISTS vector0_%q_%q;", tbl, col);
     rc = sql ? sqlite3_exec(db, sql, 0, 0, 0) : SQLITE_NOMEM;
     sqlite3_free(sql);
@@ -800,11 +820,14 @@ static int do_quantize(sqlite3_context *ctx, const char *tbl, const char *col, c
         o.vtype = v->vtype; o.dim = v->dim; o.normalized = v->normalized; o.metric = v->metric; o.qtype = v->qtype; o.max_memory = v->max_memory;
         /* NOTE: like the reference (:1429), the options start from the column's CURRENT options, so a qtype chosen by an
          * earlier AUTO run sticks unless overridden */
-        if (!options_parse(ctx, opts, &o)) return SQLITE_ERROR; /* the reference also returns with the transaction open (:1431) */
+        if (!options_parse(ctx, opts, &o)) {   /* the reference returns here with its transaction open (:1431); we undo the DROP */
+            sqlite3_exec(db, "ROLLBACK TO vsb_quantize; RELEASE vsb_quantize;", 0, 0, 0);
+            return SQLITE_ERROR;              /* options_parse has set the error message */
+        }
         rc = rebuild_quantization(ctx, v, o.qtype, o.max_memory, &counter);
     }
     if (rc != SQLITE_OK) goto fail;
-    rc = sqlite3_exec(db, "COMMIT;", 0, 0, 0);
+    rc = sqlite3_exec(db, "RELEASE vsb_quantize;", 0, 0, 0);
     if (rc != SQLITE_OK) goto fail;
     rc = meta_store(ctx, tbl, col, "qtype", 1, v->qtype, 0);
     if (rc == SQLITE_OK) rc = meta_store(ctx, tbl, col, "qscale", 0, 0, (double)v->scale);
@@ -815,7 +838,8 @@ static int do_quantize(sqlite3_context *ctx, const char *tbl, const char *col, c
     sqlite3_result_int64(ctx, (sqlite3_int64)counter);
     return SQLITE_OK;
 fail:
-    sqlite3_exec(db, "ROLLBACK;", 0, 0, 0);
+    sqlite3_exec(db, "ROLLBACK TO vsb_quantize; RELEASE vsb_quantize;", 0, 0, 0);
+    if (v->qix && !v->q_user_preloaded) { vsb_index_free(v->qix); v->qix = 0; }
     sqlite3_result_error_code(ctx, rc);
     return rc;
 }
@@ -874,7 +898,11 @@ static int stage_full_column(scan_vtab *vt, vcolumn *v) {
     sqlite3 *db = vt->db;
     sqlite3_int64 dataver = query_int64(db, "PRAGMA data_version;");
     int changes = sqlite3_total_changes(db);
-    if (v->fix && v->fix_dataver == dataver && v->fix_changes == changes) return SQLITE_OK;
+    /* Neither counter moves on ROLLBACK / ROLLBACK TO, so a copy staged while a transaction was open may hold rows that
+     * were rolled back since: such a copy is used for the query that staged it and never again.  A copy staged in
+     * autocommit mode holds committed rows only; it stays valid until a counter moves. */
+    const int in_txn = !sqlite3_get_autocommit(db);
+    if (v->fix && !v->fix_tainted && v->fix_dataver == dataver && v->fix_changes == changes) return SQLITE_OK;
     if (v->fix) { vsb_index_free(v->fix); v->fix = 0; }
     char *sql = sqlite3_mprintf("SELECT COUNT(*) FROM %q;", v->tbl);
     sqlite3_int64 total = sql ? query_int64(db, sql) : 0;
@@ -920,6 +948,7 @@ static int stage_full_column(scan_vtab *vt, vcolumn *v) {
     }
     v->fix_dataver = dataver;
     v->fix_changes = changes;
+    v->fix_tainted = in_txn;
     return SQLITE_OK;
 }
 
@@ -1007,6 +1036,21 @@ static int resident_index(scan_vtab *vt, vcolumn *v, const char *tbl, const char
         sqlite3_free(name);
         if (!exists)
             return vtab_error(&vt->base, "Quantization table not found for table '%s' and column '%s'. Ensure that vector_quantize() has been called before using vector_quantize_scan().", tbl, col);
+        if (v->qix && !v->q_user_preloaded) {
+            /* lazily staged copy = a cache of the shadow table, which the reference reads per query (:2186-2227): drop it when
+             * it was staged inside a transaction (rollbacks are invisible) or another connection rewrote the chunks */
+            int stale = v->q_tainted;
+            if (!stale) {
+                sqlite3_int64 dv = query_int64(vt->db, "PRAGMA data_version;");
+                if (dv != v->q_dataver) {
+                    sqlite3_int64 fp[4];
+                    quant_fingerprint(vt->db, v, fp);
+                    stale = memcmp(fp, v->q_fp, sizeof fp) != 0;
+                    v->q_dataver = dv;
+                }
+            }
+            if (stale) { vsb_index_free(v->qix); v->qix = 0; column_load_meta(vt->db, v); }
+        }
         if (!v->qix) { /* not preloaded: the reference streams the chunks from disk per query (:2186-2227); we stage them once */
             char *err = 0;
             if (stage_quantized(vt->db, v, &err) != SQLITE_OK) {

@@ -90,7 +90,7 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 
-if __name__ == "__main__" and "--sql" not in sys.argv:
+if __name__ == "__main__" and "--sql" not in sys.argv and "--c1" not in sys.argv:
     main()
 
 
@@ -108,3 +108,19 @@ def sql_golden():
 
 if __name__ == "__main__" and "--sql" in sys.argv:
     sql_golden()
+
+
+def c1_golden():
+    """BASELINE config 1 (vector_full_scan L2 f32 dim=384 n=100k k=20) through SQL on the unmodified reference (stock build)"""
+    import json
+    from tests.sqlrun import REF_CPU, run_c1
+    res = run_c1(REF_CPU)
+    keep = {"full": res["full"], "quant": res["quant"], "quantized_rows": res["quantized_rows"],
+            "config": {"n": 100000, "dim": 384, "k": 20, "nq": 3, "metric": "L2", "rowids": "3*i+1", "seeds": [1234, 4321]}}
+    with open(os.path.join(OUT, "sql_c1.json"), "w") as f:
+        json.dump(keep, f)
+    print("sql_c1.json", os.path.getsize(os.path.join(OUT, "sql_c1.json")), "bytes; reference ms per full scan", res["ms_full"], "quant", res["ms_quant"])
+
+
+if __name__ == "__main__" and "--c1" in sys.argv:
+    c1_golden()

@@ -50,3 +50,46 @@ REF_CPU = os.path.join(ROOT, "oracle", "_ref", "cpu", "vector")
 
 def blob(a):
     return {"hex": a.tobytes().hex()}
+
+
+# BASELINE config 1 through SQL: the child builds the table itself (100k x 384 f32 would be 300 MB of hex over a pipe)
+C1_CHILD = r'''
+import json, sqlite3, sys, time
+import numpy as np
+lib, n, dim, k, nq, metric = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6]
+x = np.random.Generator(np.random.PCG64(1234)).standard_normal((n, dim), dtype=np.float32)
+q = np.random.Generator(np.random.PCG64(4321)).standard_normal((nq, dim), dtype=np.float32)
+con = sqlite3.connect(":memory:", isolation_level=None)
+con.enable_load_extension(True)
+con.load_extension(lib)
+con.execute("CREATE TABLE c1 (id INTEGER PRIMARY KEY, e BLOB)")
+con.execute(f"SELECT vector_init('c1', 'e', 'type=FLOAT32,dimension={dim},distance={metric}')")
+con.execute("BEGIN")
+con.executemany("INSERT INTO c1(id, e) VALUES (?, ?)", ((3 * i + 1, x[i].tobytes()) for i in range(n)))
+con.execute("COMMIT")
+out = {"full": [], "quant": [], "ms_full": [], "ms_quant": []}
+for b in range(nq):
+    t0 = time.perf_counter()
+    rows = con.execute("SELECT id, distance FROM vector_full_scan('c1', 'e', ?, ?)", (q[b].tobytes(), k)).fetchall()
+    out["ms_full"].append((time.perf_counter() - t0) * 1e3)
+    out["full"].append(rows)
+out["quantized_rows"] = con.execute("SELECT vector_quantize('c1', 'e')").fetchall()[0][0]
+con.execute("SELECT vector_quantize_preload('c1', 'e')")
+for b in range(nq):
+    t0 = time.perf_counter()
+    rows = con.execute("SELECT id, distance FROM vector_quantize_scan('c1', 'e', ?, ?)", (q[b].tobytes(), k)).fetchall()
+    out["ms_quant"].append((time.perf_counter() - t0) * 1e3)
+    out["quant"].append(rows)
+print("\n@@JSON@@" + json.dumps(out), flush=True)
+'''
+
+
+def run_c1(lib_path: str, n=100_000, dim=384, k=20, nq=3, metric="L2", timeout=900):
+    """vector_full_scan / vector_quantize_scan top-k of `nq` seeded queries over a seeded n x dim f32 table, through SQL"""
+    p = subprocess.run([sys.executable, "-c", C1_CHILD, lib_path, str(n), str(dim), str(k), str(nq), metric], capture_output=True, text=True, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError(f"c1 child failed: {p.stderr[-2000:]}")
+    for ln in p.stdout.splitlines():
+        if ln.startswith("@@JSON@@"):
+            return json.loads(ln[len("@@JSON@@"):])
+    raise RuntimeError("no result line from c1 child: " + p.stdout[-500:])

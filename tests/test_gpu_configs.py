@@ -1,4 +1,5 @@
-"""BASELINE.json config 5 in miniature (all 5 metrics x 5 dtypes, dims 128/384, n = 200k, batch 1) plus the
+"""BASELINE.json config 5 in miniature (all 5 metrics x 5 dtypes, dims 128/384, n = 200k, batch 1; the stated size n = 1M x
+dims {128,384,768,1536} runs in tests/test_gpu_at_size.py) plus the
 recall of the int8-quantized scan against the exact f32 scan (the reference's own validation recipe,
 QUANTIZATION.md:41-73).  -m gpu."""
 import numpy as np

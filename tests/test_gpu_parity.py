@@ -245,3 +245,125 @@ def test_group_launch_equals_single_queries(eng, oracle, vtype, dim, n):
             assert np.array_equal(got[b][0], want[b][0]) and np.array_equal(got[b][1], want[b][1]), (vtype, metric, k, b)
     eng.set_option("fuse_mb", old_fuse)
     ix.close()
+
+
+def test_k_sequence_on_one_index(eng, oracle):
+    """the scan workspace never shrinks, so a k <= 32 query after a 33 <= k <= 256 one used to run the
+    generic list layout against the k <= 32 filter.  Every k of the sequence must match the oracle on ONE index, through
+    the synchronous call and through submit/collect."""
+    rng = np.random.Generator(np.random.PCG64(4242))
+    n, dim = 60000, 64
+    x = rng.integers(-30, 31, (n, dim)).astype(np.int8)
+    rowids = np.arange(n, dtype=np.int64) * 2 + 3
+    ix = make_index(po.I8, x, rowids)
+    for i, k in enumerate([100, 10, 33, 20, 256, 5, 32, 64, 1, 300, 7]):
+        q = rng.integers(-30, 31, dim).astype(np.int8)
+        metric = METRICS[i % len(METRICS)]
+        want_ids, want_d = oracle.scan_dense(metric, po.I8, q, x, rowids, k)
+        (res,) = ix.scan_topk(metric, q, k)
+        assert np.array_equal(res[0], want_ids) and np.array_equal(res[1], want_d), ("sync", k)
+        if k <= 256:
+            slot = ix.scan_submit(metric, q, k, on_device=False, fetch=True)
+            ids, d = ix.collect(slot, k)
+            assert np.array_equal(ids, want_ids) and np.array_equal(d, want_d), ("submit", k)
+    ix.close()
+
+
+def _special_matrix(vtype, rng, n=96, dim=40):
+    """rows with NaN / +-Inf / zero vectors / mixed-sign infinities at assorted positions (storage bits of `vtype`)"""
+    x = po.convert(rng.standard_normal((n, dim), dtype=np.float32), vtype)
+    if vtype == po.F32:
+        NAN, PINF, NINF = np.float32(np.nan), np.float32(np.inf), np.float32(-np.inf)
+    elif vtype == po.F16:
+        NAN, PINF, NINF = 0x7E00, 0x7C00, 0xFC00
+    else:
+        NAN, PINF, NINF = 0x7FC0, 0x7F80, 0xFF80
+    x[3, 2] = NAN
+    x[5, 1] = PINF
+    x[6, 7] = NINF
+    x[9, :] = 0
+    x[11, 4] = PINF; x[11, 30] = NINF            # mixed-sign infinities in one row (round-1 deviation 6)
+    x[12, 30] = PINF; x[12, 4] = NINF
+    x[13, 0] = NAN; x[13, 5] = PINF
+    x[14, 3] = PINF; x[14, 9] = NAN; x[14, 20] = NINF
+    x[15, 39] = NINF                              # last element (tail loop of the reference)
+    x[16, 8] = PINF; x[16, 9] = PINF
+    return x, (NAN, PINF, NINF)
+
+
+@pytest.mark.parametrize("vtype", [po.F32, po.F16, po.BF16])
+def test_special_values_all_fp_types(eng, oracle, vtype):
+    """NaN / Inf policies of the reference's fp kernels (distance-cpu.c:39-159 f32, :164-314 bf16, :318-466 f16), including
+    rows that mix infinities of both signs and queries that carry specials themselves: bit pattern of the result class
+    (NaN / +Inf / -Inf) identical, finite values within 1e-5."""
+    rng = np.random.Generator(np.random.PCG64(50 + vtype))
+    x, (NAN, PINF, NINF) = _special_matrix(vtype, rng)
+    dim = x.shape[1]
+    queries = [x[0].copy(), x[5].copy(), x[11].copy(), x[9].copy()]
+    qz = x[1].copy(); qz[4] = 0; qz[30] = 0      # zeros where rows 11/12 hold infinities: Inf * 0
+    queries.append(qz)
+    qn = x[2].copy(); qn[8] = NAN; qn[3] = NINF
+    queries.append(qn)
+    ix = make_index(vtype, x)
+    for qi, q in enumerate(queries):
+        for metric in METRICS:
+            got = ix.scan_all(metric, q)
+            want = oracle.distances_all(metric, vtype, q, x)
+            same_class = (np.isnan(got) == np.isnan(want)) & (np.isposinf(got) == np.isposinf(want)) & (np.isneginf(got) == np.isneginf(want))
+            assert same_class.all(), (vtype, metric, qi, np.nonzero(~same_class)[0], got[~same_class], want[~same_class])
+            fin = np.isfinite(want)
+            assert np.all(np.abs(got[fin] - want[fin]) <= 1e-5 * np.maximum(np.abs(want[fin]), 1.0)), (vtype, metric, qi)
+            # and the top-k built from them (NaN never enters, -Inf sorts first)
+            (res,) = ix.scan_topk(metric, q, 10)
+            want_ids, want_d = oracle.scan_dense(metric, vtype, q, x, np.arange(1, x.shape[0] + 1, dtype=np.int64), 10)
+            assert len(res[0]) == len(want_ids)
+            assert np.array_equal(np.isinf(res[1]), np.isinf(want_d)) and np.array_equal(np.sign(res[1][np.isinf(res[1])]), np.sign(want_d[np.isinf(want_d)]))
+    ix.close()
+
+
+@pytest.mark.parametrize("vtype", [po.F16, po.BF16])
+def test_special_values_through_the_batch_path(eng, oracle, vtype):
+    """the tensor-core path must hand rows with NaN / Inf scores to the exact refinement: same result classes as the oracle"""
+    rng = np.random.Generator(np.random.PCG64(150 + vtype))
+    n, dim, nq, k = 20000, 40, 32, 12
+    x = po.convert(rng.standard_normal((n, dim), dtype=np.float32), vtype)
+    xs, _ = _special_matrix(vtype, rng, 96, dim)
+    x[5000:5096] = xs
+    q = po.convert(rng.standard_normal((nq, dim), dtype=np.float32), vtype)
+    q[3] = xs[11]; q[4] = xs[5]
+    ix = make_index(vtype, x)
+    rowids = np.arange(1, n + 1, dtype=np.int64)
+    for metric in (po.L2, po.COS, po.DOT):
+        b0 = ix.stat("batches")
+        res = ix.scan_topk(metric, q, k)
+        assert ix.stat("batches") == b0 + 1
+        for b in range(nq):
+            want_ids, want_d = oracle.scan_dense(metric, vtype, q[b], x, rowids, k)
+            got_ids, got_d = res[b]
+            assert len(got_d) == len(want_d), (vtype, metric, b)
+            inf = np.isinf(want_d)
+            assert np.array_equal(np.isinf(got_d), inf) and np.array_equal(np.sign(got_d[inf]), np.sign(want_d[inf])), (vtype, metric, b, got_d, want_d)
+            assert set(got_ids[inf].tolist()) == set(want_ids[inf].tolist())
+            fin = ~inf
+            scale = np.maximum(np.abs(want_d[fin]), 1.0 if metric in (po.COS, po.DOT) else 1e-30)
+            assert np.all(np.abs(got_d[fin] - want_d[fin]) <= 1e-5 * scale), (vtype, metric, b)
+    ix.close()
+
+
+@pytest.mark.parametrize("vtype", [po.F32, po.F16, po.BF16])
+def test_golden_special_value_distances(eng, vtype):
+    """CUDA vs the committed outputs of the UNMODIFIED reference on NaN / Inf / signed-zero / 65504 inputs (tests/golden/
+    distances.npz, keys spa/spb/spd; no oracle in the loop): same NaN / +-Inf classes, finite values within 1e-5."""
+    g = np.load(os.path.join(G, "distances.npz"))
+    a, b = g[f"spa_{vtype}"], g[f"spb_{vtype}"]
+    ix = make_index(vtype, np.ascontiguousarray(b))
+    for m in METRICS:
+        want = g[f"spd_{vtype}_{m}"]
+        got = np.array([ix.scan_all(m, np.ascontiguousarray(a[i]))[i] for i in range(a.shape[0])], dtype=np.float32)
+        # the golden values are raw kernel results; the scan applies the nearly-zero clamp on top (sqlite-vector.c:2099)
+        want = np.where(np.abs(want) <= 8 * np.finfo(np.float32).eps, np.float32(0), want)
+        same = (np.isnan(got) == np.isnan(want)) & (np.isposinf(got) == np.isposinf(want)) & (np.isneginf(got) == np.isneginf(want))
+        assert same.all(), (vtype, m, np.nonzero(~same)[0], got[~same], want[~same])
+        fin = np.isfinite(want)
+        assert np.all(np.abs(got[fin] - want[fin]) <= 1e-5 * np.maximum(np.abs(want[fin]), 1.0)), (vtype, m)
+    ix.close()

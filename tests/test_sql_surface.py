@@ -170,3 +170,78 @@ def test_batch_tvf_equals_single_query_functions():
     js = r[-2]["rows"]
     assert [row[2] for row in js if row[0] == 1] == [row[1] for row in r[base + 2]["rows"][:3]]     # k=3 vs the head of k=7: same distances
     assert r[-1]["rows"] == [[0]]
+
+
+@pytest.mark.gpu
+def test_config1_through_sql_matches_reference_golden():
+    """BASELINE config 1 at its stated size: vector_full_scan L2 f32 dim=384 n=100k k=20 through SQL, against the output of the
+    unmodified reference extension (tests/golden/make_golden.py --c1): rowids exact, distances within 1e-5 relative; the
+    int8 quantize + preload + vector_quantize_scan leg on the same table: bit-exact."""
+    from tests.sqlrun import run_c1
+    want = json.load(open(os.path.join(G, "sql_c1.json")))
+    got = run_c1(OURS)
+    assert got["quantized_rows"] == want["quantized_rows"] == 100000
+    for b, (a, w) in enumerate(zip(got["full"], want["full"])):
+        assert [r[0] for r in a] == [r[0] for r in w], ("full", b)
+        assert all(abs(x[1] - y[1]) <= 1e-5 * abs(y[1]) for x, y in zip(a, w)), ("full", b)
+    for b, (a, w) in enumerate(zip(got["quant"], want["quant"])):
+        assert a == w, ("quant", b)
+
+
+@pytest.mark.gpu
+def test_k_sequence_and_transactions_through_sql():
+    """(1) ADVICE r1 high: k=100 then k=10 then k=33 on one connection; (2) ADVICE r1 medium: a scan inside a transaction
+    sees the uncommitted row, a scan after ROLLBACK / ROLLBACK TO must not; (3) vector_quantize nests inside a caller's
+    transaction (savepoint) and its lazily staged chunks do not survive a ROLLBACK."""
+    import numpy as np
+
+    from oracle import pyoracle as po
+    rng = np.random.Generator(np.random.PCG64(11))
+    n, dim = 3000, 16
+    x = rng.integers(-40, 41, (n, dim)).astype(np.int8)
+    ids = np.arange(n, dtype=np.int64) * 2 + 1
+    q = rng.integers(-40, 41, dim).astype(np.int8)
+    qb = {"hex": q.tobytes().hex()}
+    s = ["CREATE TABLE t (id INTEGER PRIMARY KEY, e BLOB)", "CREATE TABLE other (v)", f"SELECT vector_init('t','e','type=INT8,dimension={dim}')"]
+    s += [["INSERT INTO t(id, e) VALUES (?, ?)", [int(ids[i]), {"hex": x[i].tobytes().hex()}]] for i in range(n)]
+    mark = len(s)
+    s += [["SELECT id, distance FROM vector_full_scan('t','e',?,100)", [qb]],        # 0
+          ["SELECT id, distance FROM vector_full_scan('t','e',?,10)", [qb]],         # 1
+          ["SELECT id, distance FROM vector_full_scan('t','e',?,33)", [qb]],         # 2
+          "BEGIN",                                                                   # 3
+          ["INSERT INTO t(id, e) VALUES (100001, ?)", [qb]],                         # 4  distance 0 to the query
+          ["SELECT id, distance FROM vector_full_scan('t','e',?,3)", [qb]],          # 5  sees it
+          "ROLLBACK",                                                                # 6
+          ["SELECT id, distance FROM vector_full_scan('t','e',?,3)", [qb]],          # 7  must not
+          "BEGIN", "SAVEPOINT sp",                                                   # 8 9
+          ["INSERT INTO t(id, e) VALUES (100002, ?)", [qb]],                         # 10
+          ["SELECT id, distance FROM vector_full_scan('t','e',?,3)", [qb]],          # 11 sees it
+          "ROLLBACK TO sp",                                                          # 12
+          ["SELECT id, distance FROM vector_full_scan('t','e',?,3)", [qb]],          # 13 must not
+          "INSERT INTO other VALUES (1)",                                            # 14 unrelated write
+          ["SELECT id, distance FROM vector_full_scan('t','e',?,3)", [qb]],          # 15
+          "COMMIT",                                                                  # 16
+          "BEGIN", "SELECT vector_quantize('t','e')",                                # 17 18 nests (reference: fails + rolls the caller back)
+          ["SELECT id, distance FROM vector_quantize_scan('t','e',?,5)", [qb]],      # 19 lazily staged inside the transaction
+          "ROLLBACK",                                                                # 20 shadow table gone again
+          ["SELECT id, distance FROM vector_quantize_scan('t','e',?,5)", [qb]],      # 21 error: not quantized
+          "SELECT vector_quantize('t','e','qtype=BOGUS')",                           # 22 error, transaction state intact
+          "SELECT vector_quantize('t','e')",                                         # 23
+          ["SELECT id, distance FROM vector_quantize_scan('t','e',?,5)", [qb]],      # 24
+          ]
+    r = run_sql(OURS, s)[mark:]
+    orc = po.Oracle()
+
+    def want(k, xs=x, rid=ids):
+        a, d = orc.scan_dense(po.L2, po.I8, q, xs, rid, k)
+        return [[int(i), float(v)] for i, v in zip(a, d)]
+    assert r[0]["rows"] == want(100) and r[1]["rows"] == want(10) and r[2]["rows"] == want(33)
+    assert r[5]["rows"][0] == [100001, 0.0]
+    assert r[7]["rows"] == want(3), "rolled-back row served from the device copy"
+    assert r[11]["rows"][0] == [100002, 0.0]
+    assert r[13]["rows"] == want(3) and r[15]["rows"] == want(3)
+    assert r[18] == {"rows": [[n]]}, r[18]
+    assert len(r[19]["rows"]) == 5
+    assert "Quantization table not found" in r[21].get("error", ""), r[21]
+    assert "Invalid quantization type" in r[22].get("error", "")
+    assert r[23] == {"rows": [[n]]} and r[24]["rows"] == r[19]["rows"]
