@@ -157,6 +157,43 @@ VSB_API int vsb_batch_merge(vsb_index *ix, const void *d_blocks, int world, int6
                             int k, int64_t *out_seq, double *out_dist, int *out_counts);
 /* out[i] = rowid of global row seq[i] when this shard owns it, else 0 (so shards can be summed) */
 VSB_API int vsb_index_lookup_rowids(const vsb_index *ix, const int64_t *seq, int64_t n, int64_t *out);
+/* ---- exchange over NVLink peer memory: one process per GPU (torchrun), no collective library on the data path -----------
+ * The final all-gather of the shards' per-query result heads (north_star "final allgather of per-shard top-k over
+ * NVLink") is fused into the filter kernel: the block that completes a head stores it into row `rank` of EVERY peer's gather
+ * buffer (cudaIpc-mapped peer memory) and raises an arrival flag; the receiver waits on the flags on its own stream and
+ * copies the gathered heads to pinned host memory once per group.
+ * setup (once): every rank calls vsb_exchange_export (allocates its gather buffer, returns a 64-byte cudaIpc handle), the
+ * launcher all-gathers the handles (any transport: they are 64 bytes), every rank calls vsb_exchange_attach with all of them.
+ * per group of 1..8 independent queries (the same call sequence on every rank): vsb_exchange_submit launches scan + filter
+ * (+ push) and the receive; vsb_exchange_collect waits for the group and replays the reference's slot algorithm
+ * (src/sqlite-vector.c:2145-2152, 2022-2069) over the shards in scan order — every rank gets the same complete result.
+ * Slots are first_slot .. first_slot + nq - 1 of vsb_index_stat("slots"); a rank may have at most slots/2 queries in flight. */
+VSB_API int vsb_exchange_export(vsb_index *ix, int world, int rank, void *handle64);
+VSB_API int vsb_exchange_attach(vsb_index *ix, const void *handles /* world x 64 bytes, in rank order */);
+VSB_API int vsb_exchange_submit(vsb_index *ix, int metric, const void *queries, int64_t query_stride, int nq, int query_on_device,
+                                int k, int first_slot);
+VSB_API int vsb_exchange_collect(vsb_index *ix, int first_slot, int nq, const int64_t *first_seq /* [world] */, int k,
+                                 int64_t *out_rowids, double *out_dist, int *out_counts);
+
+/* ---- shard group: ONE column row-sharded over several GPUs inside one process (the SQLite extension, option gpus=N) --------
+ * Replaces table_context.preloaded (src/sqlite-vector.c:135-136) by `ngpus` resident shards of contiguous row ranges in scan
+ * order: shard s holds rows [capacity*s/ngpus, capacity*(s+1)/ngpus).  Rows are appended in scan order exactly like the
+ * single-index calls; scans have the contract of vsb_scan_topk / vsb_scan_all.  Every shard's filter pushes its head to the
+ * leader GPU over NVLink peer memory (cudaDeviceEnablePeerAccess); batched queries gather the shards' entry logs with
+ * cudaMemcpyPeerAsync and merge on the leader.  ngpus == 1 is exactly a vsb_index. */
+typedef struct vsb_group vsb_group;
+VSB_API int vsb_group_create(vsb_group **out, int first_device, int ngpus, int vtype, int dim, int64_t capacity_rows);
+VSB_API int vsb_group_append_dense(vsb_group *g, const void *vectors, const int64_t *rowids, int64_t nrows);
+VSB_API int vsb_group_append_quant_chunk(vsb_group *g, const void *chunk, int64_t nrows);
+VSB_API int vsb_group_finalize(vsb_group *g);
+VSB_API int vsb_group_scan_topk(vsb_group *g, int metric, const void *queries, int nq, int k, int64_t *out_rowids, double *out_dist,
+                                int *out_counts, int *max_index);
+VSB_API int vsb_group_scan_all(vsb_group *g, int metric, const void *query, float *out_dist, int64_t *out_rowids);
+VSB_API int vsb_group_gpus(const vsb_group *g);
+VSB_API int64_t vsb_group_rows(const vsb_group *g);
+VSB_API vsb_index *vsb_group_shard(vsb_group *g, int shard); /* borrowed; for statistics */
+VSB_API void vsb_group_free(vsb_group *g);
+
 VSB_API int vsb_index_query_pitch(const vsb_index *ix); /* bytes per query row on the device (multiple of 16) */
 /* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes","slots","batches","batch_cands","batch_kept","tc_us","tc_rows","batch_us"}; -1 if unknown */
 VSB_API int64_t vsb_index_stat(const vsb_index *ix, const char *name);
@@ -169,7 +206,8 @@ VSB_API int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches,
 /* diagnostics: copies an internal device buffer of the most recent single-query scan to `out`; name in {"cta_time" (unsigned
  * cycles per scan CTA), "bounds" (int64 tile boundaries of the adaptive row partition)}.  Returns the bytes copied or < 0. */
 VSB_API int vsb_debug_read(vsb_index *ix, const char *name, void *out, int64_t bytes);
-/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat","epi2","batch_debug","batch_m0","batch_growth","balance","fuse_mb","epi_max" (experimental),"tc_n" (experimental)}; returns previous value */
+/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat","epi2","batch_debug","batch_m0","batch_growth","balance","fuse_mb","scan_streams","xwait_ms","epi_max" (experimental),"tc_n" (experimental)};
+ * values are non-negative; returns the previous value, or a negative VSB_E* code (unknown name, negative value) */
 VSB_API int vsb_set_option(const char *name, int value);
 
 #ifdef __cplusplus

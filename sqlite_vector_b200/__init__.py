@@ -3,10 +3,10 @@
 The product is the pair of shared libraries built from csrc/ (see include/vsb200.h):
   lib/libvsb200.so  C-ABI scan engine (hand-written sm_100a CUDA)
   lib/vector.so     SQLite loadable extension (entry point sqlite3_vector_init) + the engine
-This package is the thin host-side mirror used by tests and bench.py: ctypes bindings (api.py),
-an sqlite3 loader (sql.py) and the torch.distributed row-shard driver (shard.py).
+This package is the thin host-side mirror used by tests and bench.py: ctypes bindings (api.py) and the
+torch.distributed row-shard driver (shard.py: one process per GPU; the heads travel over NVLink peer memory).
 There is no CPU fallback anywhere in this package.
 """
-from .api import Engine, Index, VsbError, load_engine  # noqa: F401
+from .api import Engine, Group, Index, VsbError, load_engine  # noqa: F401
 
-__all__ = ["Engine", "Index", "VsbError", "load_engine"]
+__all__ = ["Engine", "Group", "Index", "VsbError", "load_engine"]

@@ -15,7 +15,14 @@ ELEM_SIZE = {F32: 4, F16: 2, BF16: 2, U8: 1, I8: 1}
 
 
 class VsbError(RuntimeError):
-    pass
+    """rc: the VSB_E* code (callers fall back on VSB_ERANGE only; everything else is a real failure)"""
+
+    def __init__(self, msg, rc: int = -1):
+        super().__init__(msg)
+        self.rc = rc
+
+
+EINVAL, ENODEV, ENOMEM, ECUDA, ERANGE = -1, -2, -3, -4, -5
 
 
 class Candidate(C.Structure):
@@ -53,6 +60,20 @@ _SIGNATURES = {
     "vsb_batch_shard_scan": (_i, [_vp, _i, _vp, _i, _i, C.POINTER(_vp), C.POINTER(_i64)]),
     "vsb_batch_merge": (_i, [_vp, _vp, _i, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     "vsb_index_lookup_rowids": (_i, [_vp, _vp, _i64, _vp]),
+    "vsb_exchange_export": (_i, [_vp, _i, _i, _vp]),
+    "vsb_exchange_attach": (_i, [_vp, _vp]),
+    "vsb_exchange_submit": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _i]),
+    "vsb_exchange_collect": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "vsb_group_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i64]),
+    "vsb_group_append_dense": (_i, [_vp, _vp, _vp, _i64]),
+    "vsb_group_append_quant_chunk": (_i, [_vp, _vp, _i64]),
+    "vsb_group_finalize": (_i, [_vp]),
+    "vsb_group_scan_topk": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "vsb_group_scan_all": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "vsb_group_gpus": (_i, [_vp]),
+    "vsb_group_rows": (_i64, [_vp]),
+    "vsb_group_shard": (_vp, [_vp, _i]),
+    "vsb_group_free": (None, [_vp]),
     "vsb_index_query_pitch": (_i, [_vp]),
     "vsb_index_stream": (_vp, [_vp]),
     "vsb_index_stat": (_i64, [_vp, C.c_char_p]),
@@ -85,7 +106,7 @@ class Engine:
 
     def check(self, rc: int):
         if rc != 0:
-            raise VsbError(f"vsb error {rc}: {self.lib.vsb_last_error().decode()}")
+            raise VsbError(f"vsb error {rc}: {self.lib.vsb_last_error().decode()}", rc)
 
     def device_count(self) -> int:
         return self.lib.vsb_device_count()
@@ -262,6 +283,28 @@ class Index:
         self.eng.check(self.eng.lib.vsb_index_lookup_rowids(self.h, _ptr(sq), sq.size, _ptr(out)))
         return out
 
+    # ---- exchange over NVLink peer memory (one process per GPU)
+    def exchange_export(self, world: int, rank: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        self.eng.check(self.eng.lib.vsb_exchange_export(self.h, world, rank, C.cast(h, C.c_void_p)))
+        return bytes(h)
+
+    def exchange_attach(self, handles: bytes):
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        self.eng.check(self.eng.lib.vsb_exchange_attach(self.h, C.cast(buf, C.c_void_p)))
+
+    def exchange_submit(self, metric: int, queries, stride: int, nq: int, k: int, on_device: bool, first_slot: int):
+        ptr = int(queries) if on_device else _ptr(queries)
+        self.eng.check(self.eng.lib.vsb_exchange_submit(self.h, metric, ptr, stride, nq, int(on_device), k, first_slot))
+
+    def exchange_collect(self, first_slot: int, nq: int, first_seq: np.ndarray, k: int):
+        ids = np.zeros((nq, max(k, 1)), dtype=np.int64)
+        dist = np.zeros((nq, max(k, 1)), dtype=np.float64)
+        counts = np.zeros(nq, dtype=np.int32)
+        fs = np.ascontiguousarray(first_seq, dtype=np.int64)
+        self.eng.check(self.eng.lib.vsb_exchange_collect(self.h, first_slot, nq, _ptr(fs), k, _ptr(ids), _ptr(dist), _ptr(counts)))
+        return [(ids[j, :counts[j]], dist[j, :counts[j]]) for j in range(nq)]
+
     def collect(self, slot: int, k: int):
         ids = np.zeros(max(k, 1), dtype=np.int64)
         dist = np.zeros(max(k, 1), dtype=np.float64)
@@ -291,3 +334,59 @@ class Index:
         cnt = C.c_int(0)
         self.eng.check(self.eng.lib.vsb_collect_last(self.h, k, _ptr(ids), _ptr(dist), C.byref(cnt)))
         return ids[:cnt.value].copy(), dist[:cnt.value].copy()
+
+
+class Group:
+    """One column row-sharded over several GPUs inside ONE process (what the SQLite extension uses with gpus=N)."""
+
+    def __init__(self, vtype: int, dim: int, capacity: int, ngpus: int, first_device: int = 0, engine: Engine | None = None):
+        self.eng = engine or load_engine()
+        self.vtype, self.dim = vtype, dim
+        h = _vp()
+        self.eng.check(self.eng.lib.vsb_group_create(C.byref(h), first_device, ngpus, vtype, dim, capacity))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.eng.lib.vsb_group_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def gpus(self) -> int:
+        return int(self.eng.lib.vsb_group_gpus(self.h))
+
+    @property
+    def rows(self) -> int:
+        return int(self.eng.lib.vsb_group_rows(self.h))
+
+    def append_dense(self, vectors: np.ndarray, rowids: np.ndarray | None = None):
+        rid = None if rowids is None else np.ascontiguousarray(rowids, dtype=np.int64)
+        self.eng.check(self.eng.lib.vsb_group_append_dense(self.h, _ptr(np.ascontiguousarray(vectors)), _ptr(rid), vectors.shape[0]))
+
+    def append_quant_chunk(self, chunk: np.ndarray, nrows: int):
+        self.eng.check(self.eng.lib.vsb_group_append_quant_chunk(self.h, _ptr(chunk), nrows))
+
+    def finalize(self):
+        self.eng.check(self.eng.lib.vsb_group_finalize(self.h))
+
+    def scan_topk(self, metric: int, queries: np.ndarray, k: int, max_index: int | None = None):
+        q = np.ascontiguousarray(queries)
+        q2 = q.reshape(-1, q.shape[-1]) if q.ndim > 1 else q.reshape(1, -1)
+        nq = q2.shape[0]
+        ids = np.zeros((nq, max(k, 1)), dtype=np.int64)
+        dist = np.zeros((nq, max(k, 1)), dtype=np.float64)
+        counts = np.zeros(nq, dtype=np.int32)
+        mi = C.c_int(0 if max_index is None else max_index)
+        self.eng.check(self.eng.lib.vsb_group_scan_topk(self.h, metric, _ptr(q2), nq, k, _ptr(ids), _ptr(dist), _ptr(counts),
+                                                       C.byref(mi) if max_index is not None else None))
+        out = [(ids[b, :counts[b]].copy(), dist[b, :counts[b]].copy()) for b in range(nq)]
+        return (out, mi.value) if max_index is not None else out
+
+    def scan_all(self, metric: int, query: np.ndarray, want_rowids: bool = False):
+        n = self.rows
+        dist = np.zeros(n, dtype=np.float32)
+        ids = np.zeros(n, dtype=np.int64) if want_rowids else None
+        self.eng.check(self.eng.lib.vsb_group_scan_all(self.h, metric, _ptr(np.ascontiguousarray(query)), _ptr(dist), _ptr(ids)))
+        return (dist, ids) if want_rowids else dist

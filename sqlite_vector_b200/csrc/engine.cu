@@ -48,6 +48,10 @@ int g_opt_tc_n = 0;            // 128: EXPERIMENTAL 128-query tensor-core tiles 
 int g_opt_epi_max = 0;         // 1: EXPERIMENTAL running-maximum pre-test in the int8/uint8 L2 / DOT tensor-core epilogue (not validated on a GPU yet)
 int g_opt_epi2 = 2;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 2 = 8 epilogue warps, two per TMEM lane quadrant
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
+int g_opt_scan_streams = 2;    // 2: consecutive scan launches alternate between two streams, so the CTAs of launch i+1 take over each SM
+                               // as soon as the CTA of launch i on it exits (one scan CTA fits per SM): no grid-wide drain between
+                               // launches, per-SM speed differences turn into an earlier start of the next query.  1: one stream.
+int g_opt_xwait_ms = 2000;     // exchange: how long the receiving side waits for a peer's head before it reports an error
 
 // cudaFuncSetAttribute costs ~1 us per call; the dynamic shared memory limit of a kernel only ever needs to grow
 int set_smem_limit(const void *fn, size_t bytes) {
@@ -100,7 +104,8 @@ int elem_size(int vtype) {
 constexpr size_t kStageBuf = 32u << 20;  // pinned staging buffers for preload (two of them)
 constexpr int kOutCap = 1 << 16;         // survivor capacity per query (mapped pinned)
 constexpr int kMaxK = 256;               // candidate path; larger k uses the all-distances path
-constexpr int kSlots = 16;               // result slots: queries in flight (the sharded exchange gathers groups of them)
+constexpr int kSlots = 32;               // result slots: queries in flight (the sharded exchange moves groups of them; a rank may have at most
+                                         // kSlots / 2 queries in flight so that a peer never overwrites a gather row that is still being read)
 
 // result block of one query, written by filter_kernel into DEVICE memory and fetched with one async copy:
 //   head = [hdr: 16 ints][table: kTableCap x int2][first kFirstFetch survivors x uint2]   (kHeadBytes, what travels)
@@ -131,12 +136,12 @@ struct Work {
     cudaEvent_t drained = nullptr;   // filter stream: the filters that read this workspace have finished
     bool in_use = false;
 };
-constexpr int kWorks = 2;
+constexpr int kWorks = 4;
 
 struct Slot {
     uint8_t *d_res = nullptr, *h_res = nullptr;      // this slot's head inside vsb_index::d_heads / h_heads
     uint2 *h_out = nullptr, *d_out = nullptr;        // first kFirstFetch survivors (inside the head)
-    uint2 *h_tail = nullptr, *d_tail = nullptr;      // survivors kFirstFetch.. (own allocations)
+    uint2 *h_tail = nullptr, *d_tail = nullptr;      // survivors kFirstFetch.. (inside vsb_index::d_tails / h_tails)
     int2 *h_table = nullptr, *d_table = nullptr;
     int *h_hdr = nullptr, *d_hdr = nullptr;
     uint8_t *h_query = nullptr, *d_query = nullptr;  // pinned staging + device copy of the query
@@ -160,11 +165,16 @@ struct vsb_index {
     int stage_next = 0;
     int num_sms = 0, max_smem = 0;
     cudaStream_t fstream = nullptr;   // filter + result copy of a query; `stream` carries staging, scans and the batch path
+    cudaStream_t stream2 = nullptr;   // second scan stream (option scan_streams = 2): single-query scans alternate between the two
+    cudaStream_t xstream = nullptr;   // exchange: flag wait + copy of the gathered heads to the host
+    int snext = 0;
+    struct Exchange *xch = nullptr;   // peer-memory exchange (multi-GPU), see exchange.inc
     // scan workspaces
     int ws_kcap = 0, ws_logcap = 0, ws_streams = 0, ws_next = 0;
     Work work[kWorks];
     Slot slot[kSlots];
     uint8_t *d_heads = nullptr, *h_heads = nullptr;   // kSlots x kHeadBytes
+    uint8_t *d_tails = nullptr, *h_tails = nullptr;   // kSlots x (kOutCap - kFirstFetch) x uint2
     bool slots_ready = false;
     float *d_dist_all = nullptr;
     int last_slot = -1, last_metric = 0;
@@ -253,41 +263,51 @@ Plan make_plan(const vsb_index *ix, int kcap) {
 }
 
 void free_slots(vsb_index *ix) {
+    if (ix->slot[0].h_query) cudaFreeHost(ix->slot[0].h_query);     // slot 0 holds the base of the shared allocations
+    if (ix->slot[0].d_query) cudaFree(ix->slot[0].d_query);
+    if (ix->slot[0].d_ctrl) cudaFree(ix->slot[0].d_ctrl);
     for (int i = 0; i < kSlots; ++i) {
         Slot &s = ix->slot[i];
-        if (s.h_tail) cudaFreeHost(s.h_tail);
-        if (s.d_tail) cudaFree(s.d_tail);
-        if (s.h_query) cudaFreeHost(s.h_query);
-        if (s.d_query) cudaFree(s.d_query);
-        if (s.d_ctrl) cudaFree(s.d_ctrl);
         if (s.done) cudaEventDestroy(s.done);
         s = Slot();
     }
     if (ix->h_heads) cudaFreeHost(ix->h_heads);
     if (ix->d_heads) cudaFree(ix->d_heads);
-    ix->h_heads = nullptr; ix->d_heads = nullptr;
+    if (ix->h_tails) cudaFreeHost(ix->h_tails);
+    if (ix->d_tails) cudaFree(ix->d_tails);
+    ix->h_heads = nullptr; ix->d_heads = nullptr; ix->h_tails = nullptr; ix->d_tails = nullptr;
     ix->slots_ready = false;
 }
 
 int ensure_slots_alloc(vsb_index *ix) {
+    const size_t tail_bytes = sizeof(uint2) * (size_t)(kOutCap - kFirstFetch);
     CU(cudaMalloc((void **)&ix->d_heads, kHeadBytes * kSlots));
     CU(cudaMemset(ix->d_heads, 0, kHeadBytes * kSlots));
     CU(cudaHostAlloc((void **)&ix->h_heads, kHeadBytes * kSlots, cudaHostAllocDefault));
     memset(ix->h_heads, 0, kHeadBytes * kSlots);
+    CU(cudaMalloc((void **)&ix->d_tails, tail_bytes * kSlots));
+    CU(cudaHostAlloc((void **)&ix->h_tails, tail_bytes * kSlots, cudaHostAllocDefault));
+    uint8_t *hq = nullptr, *dq = nullptr;                      // query staging of all slots: one pinned + one device allocation
+    int *dc = nullptr;
+    CU(cudaHostAlloc((void **)&hq, (size_t)ix->pitch * kSlots, cudaHostAllocDefault));
+    ix->slot[0].h_query = hq;
+    CU(cudaMalloc((void **)&dq, (size_t)ix->pitch * kSlots));
+    ix->slot[0].d_query = dq;
+    CU(cudaMalloc((void **)&dc, sizeof(int) * 4 * kSlots));
+    ix->slot[0].d_ctrl = dc;
+    CU(cudaMemset(dc, 0, sizeof(int) * 4 * kSlots));
     for (int i = 0; i < kSlots; ++i) {
         Slot &s = ix->slot[i];
         s.d_res = ix->d_heads + kHeadBytes * i;
         s.h_res = ix->h_heads + kHeadBytes * i;
-        const size_t tail_bytes = sizeof(uint2) * (size_t)(kOutCap - kFirstFetch);
-        CU(cudaMalloc((void **)&s.d_tail, tail_bytes));
-        CU(cudaHostAlloc((void **)&s.h_tail, tail_bytes, cudaHostAllocDefault));
+        s.d_tail = (uint2 *)(ix->d_tails + tail_bytes * i);
+        s.h_tail = (uint2 *)(ix->h_tails + tail_bytes * i);
         s.d_hdr = (int *)s.d_res; s.h_hdr = (int *)s.h_res;
         s.d_table = (int2 *)(s.d_res + 64); s.h_table = (int2 *)(s.h_res + 64);
         s.d_out = (uint2 *)(s.d_res + kResHdrBytes); s.h_out = (uint2 *)(s.h_res + kResHdrBytes);
-        CU(cudaHostAlloc((void **)&s.h_query, (size_t)ix->pitch, cudaHostAllocDefault));
-        CU(cudaMalloc((void **)&s.d_query, (size_t)ix->pitch));
-        CU(cudaMalloc((void **)&s.d_ctrl, sizeof(int) * 4));
-        CU(cudaMemset(s.d_ctrl, 0, sizeof(int) * 4));
+        s.h_query = hq + (size_t)ix->pitch * i;
+        s.d_query = dq + (size_t)ix->pitch * i;
+        s.d_ctrl = dc + 4 * i;
         CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
     return VSB_OK;
@@ -307,6 +327,7 @@ int ensure_workspace(vsb_index *ix, int k) {
     const int streams = ix->num_sms * kWarps;
     if (ix->ws_kcap >= kcap && ix->ws_logcap >= logcap && ix->ws_streams == streams) return VSB_OK;
     CU(cudaStreamSynchronize(ix->stream));       // queries in flight still use the old workspaces
+    CU(cudaStreamSynchronize(ix->stream2));
     CU(cudaStreamSynchronize(ix->fstream));
     ix->ws_kcap = 0;
     for (int i = 0; i < kWorks; ++i) {
@@ -337,11 +358,16 @@ int ensure_workspace(vsb_index *ix, int k) {
     return VSB_OK;
 }
 
+unsigned exchange_next_seq(vsb_index *ix, int slot);
+void exchange_free(vsb_index *ix);
+int exchange_fill_push(vsb_index *ix, PushParams *pp);
+
 // launches ONE scan kernel for nq independent queries (device pointers, pitch bytes each) on ix->stream and, when k > 0,
 // one filter launch (grid.y = nq) on ix->fstream.  slots[g] receives query g's result.
 // fetch: copy the slots' heads to pinned host memory afterwards (false when the heads are all-gathered on the device)
+// ss: the scan stream of this launch (next_scan_stream); push: the filter also pushes each head into the exchange targets
 int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries, int nq, int k, Slot *const *slots, float *d_dist_all,
-                      bool fetch) {
+                      bool fetch, cudaStream_t ss, bool push = false) {
     int root = 0;
     const int mc = metric_class(metric, &root);
     if (mc < 0) return fail(VSB_EINVAL, "unknown distance metric %d", metric);
@@ -357,14 +383,14 @@ int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries
     // an SM, and the filter blocks of launch i are meant to run beside the scan CTAs of launch i+1
     CU((cudaError_t)set_smem_limit((const void *)fn, pl.smem));
 
-    // the scan runs on ix->stream, the filter (+ result copy) on ix->fstream: while the filters of this launch walk the
+    // the scan runs on its scan stream (ss), the filter (+ result copy) on ix->fstream: while the filters of this launch walk the
     // k-lists and compact the candidate logs, the scan of the next launch is already streaming the shard (the filter
     // blocks are small enough to sit on the SMs beside the scan CTAs).  The two workspaces alternate.
     Work *wk = nullptr;
     if (k > 0) {
         wk = &ix->work[ix->ws_next];
         ix->ws_next = (ix->ws_next + 1) % kWorks;
-        if (wk->in_use) CU(cudaStreamWaitEvent(ix->stream, wk->drained, 0));   // its previous filters must have read it
+        if (wk->in_use) CU(cudaStreamWaitEvent(ss, wk->drained, 0));   // its previous filters must have read it
     }
     // adaptive partition (k <= 32 path only: that filter kernel maintains it): equal shares to start with
     const long long rpw = 32 >> pl.log2P;
@@ -373,8 +399,8 @@ int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries
     if (balance && wk->bounds_tiles != total_tiles) {
         std::vector<long long> b((size_t)ix->num_sms + 1);
         for (int c = 0; c <= ix->num_sms; ++c) b[(size_t)c] = (total_tiles * c) / ix->num_sms;
-        CU(cudaMemcpyAsync(wk->d_bounds, b.data(), sizeof(long long) * b.size(), cudaMemcpyHostToDevice, ix->stream));   // pageable: staged before return
-        CU(cudaMemsetAsync(wk->d_cta_time, 0, sizeof(unsigned) * (size_t)ix->num_sms, ix->stream));
+        CU(cudaMemcpyAsync(wk->d_bounds, b.data(), sizeof(long long) * b.size(), cudaMemcpyHostToDevice, ss));   // pageable: staged before return
+        CU(cudaMemsetAsync(wk->d_cta_time, 0, sizeof(unsigned) * (size_t)ix->num_sms, ss));
         wk->bounds_tiles = total_tiles;
     }
     ScanParams p{};
@@ -415,16 +441,20 @@ int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries
         ix->prof_used += 4;
         ix->prof_kind.push_back(k > 0 ? 2 : 1);
         ix->prof_nq.push_back(nq);
-        CU(cudaEventRecord(pev[0], ix->stream));
+        CU(cudaEventRecord(pev[0], ss));
     }
-    fn<<<ix->num_sms, kThreads, pl.smem, ix->stream>>>(p);
+    fn<<<ix->num_sms, kThreads, pl.smem, ss>>>(p);
     CU(cudaGetLastError());
     ++g_launches;
-    if (pev) CU(cudaEventRecord(pev[1], ix->stream));
+    if (pev) CU(cudaEventRecord(pev[1], ss));
     if (k > 0) {
-        CU(cudaEventRecord(wk->scanned, ix->stream));
+        CU(cudaEventRecord(wk->scanned, ss));
         CU(cudaStreamWaitEvent(ix->fstream, wk->scanned, 0));
         FilterParams f{};
+        if (push) {
+            const int rc = exchange_fill_push(ix, &f.push);
+            if (rc) return rc;
+        }
         f.S = ix->ws_streams;
         f.k = k;
         f.kcap = kcap;
@@ -449,6 +479,8 @@ int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries
             q.hdr = slot->d_hdr;
             q.ctrl = slot->d_ctrl;
             q.seqno = ++slot->seq;
+            q.xslot = (int)(slot - ix->slot);
+            q.xseq = push ? exchange_next_seq(ix, q.xslot) : 0u;
             slot->nblocks = nblocks;
         }
         f.bounds = balance ? wk->d_bounds : nullptr;
@@ -482,8 +514,15 @@ int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries
     return VSB_OK;
 }
 
-int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *slot, float *d_dist_all, bool fetch = true) {
-    return launch_scan_group(ix, metric, &d_query, 1, k, slot ? &slot : nullptr, d_dist_all, fetch);
+int launch_scan(vsb_index *ix, int metric, const uint8_t *d_query, int k, Slot *slot, float *d_dist_all, bool fetch, cudaStream_t ss) {
+    return launch_scan_group(ix, metric, &d_query, 1, k, slot ? &slot : nullptr, d_dist_all, fetch, ss);
+}
+
+// single-query scans alternate between two streams (option scan_streams, see g_opt_scan_streams)
+cudaStream_t next_scan_stream(vsb_index *ix) {
+    if (g_opt_scan_streams < 2) return ix->stream;
+    ix->snext ^= 1;
+    return ix->snext ? ix->stream2 : ix->stream;
 }
 
 inline int64_t rowid_of(const vsb_index *ix, uint32_t local) {
@@ -557,7 +596,7 @@ int scan_all_into(vsb_index *ix, int metric, const uint8_t *d_query, std::vector
         CU(cudaMalloc((void **)&ix->d_dist_all, sizeof(float) * (size_t)std::max<long long>(ix->cap, 1)));
         ix->dev_bytes += sizeof(float) * (size_t)ix->cap;
     }
-    int rc = launch_scan(ix, metric, d_query, 0, nullptr, ix->d_dist_all);
+    int rc = launch_scan(ix, metric, d_query, 0, nullptr, ix->d_dist_all, true, ix->stream);
     if (rc) return rc;
     dist.resize((size_t)ix->n);
     CU(cudaMemcpyAsync(dist.data(), ix->d_dist_all, sizeof(float) * (size_t)ix->n, cudaMemcpyDeviceToHost, ix->stream));
@@ -565,11 +604,11 @@ int scan_all_into(vsb_index *ix, int metric, const uint8_t *d_query, std::vector
     return VSB_OK;
 }
 
-int stage_query(vsb_index *ix, Slot *slot, const void *query) {
+int stage_query(vsb_index *ix, Slot *slot, const void *query, cudaStream_t ss) {
     const int qbytes = ix->dim * ix->esize;
     memcpy(slot->h_query, query, (size_t)qbytes);
     if (ix->pitch > qbytes) memset(slot->h_query + qbytes, 0, (size_t)(ix->pitch - qbytes));
-    CU(cudaMemcpyAsync(slot->d_query, slot->h_query, (size_t)ix->pitch, cudaMemcpyHostToDevice, ix->stream));
+    CU(cudaMemcpyAsync(slot->d_query, slot->h_query, (size_t)ix->pitch, cudaMemcpyHostToDevice, ss));
     return VSB_OK;
 }
 
@@ -580,13 +619,13 @@ int query_candidates(vsb_index *ix, int metric, const void *query, int k, std::v
     int rc = ensure_slots(ix);
     if (rc) return rc;
     Slot *slot = &ix->slot[0];
-    rc = stage_query(ix, slot, query);
+    rc = stage_query(ix, slot, query, ix->stream);   // synchronous call: one stream (a possible all-distances fallback reads d_query on it)
     if (rc) return rc;
     bool overflow = (k > kMaxK);
     if (!overflow) {
         rc = ensure_workspace(ix, k);
         if (rc) return rc;
-        rc = launch_scan(ix, metric, slot->d_query, k, slot, nullptr);
+        rc = launch_scan(ix, metric, slot->d_query, k, slot, nullptr, true, ix->stream);
         if (rc) return rc;
         CU(cudaEventSynchronize(slot->done));
         int n = gather_survivors(ix, slot, cands, &overflow);
@@ -612,9 +651,49 @@ int check_index(const vsb_index *ix) {
     return VSB_OK;
 }
 
+// scan + filter launches for a group of independent queries (query j at queries + j * query_stride; slots first_slot ..).
+// push: the heads also travel to the exchange targets (peer memory), see exchange.inc
+int submit_group(vsb_index *ix, int metric, const void *queries, int64_t query_stride, int nq, int query_on_device, int k, int fetch,
+                 int first_slot, bool push) {
+    if (check_index(ix)) return VSB_EINVAL;
+    if (!queries || k <= 0 || k > kMaxK) return fail(VSB_EINVAL, "bad scan arguments (k must be 1..%d)", kMaxK);
+    if (nq <= 0 || first_slot < 0 || first_slot + nq > kSlots) return fail(VSB_EINVAL, "bad slot group [%d, %d)", first_slot, first_slot + nq);
+    CU(cudaSetDevice(ix->device));
+    int rc = ensure_slots(ix);
+    if (rc) return rc;
+    rc = ensure_workspace(ix, k);
+    if (rc) return rc;
+    const bool fuse = (double)ix->n * ix->pitch < (double)g_opt_fuse_mb * 1048576.0;
+    const int per_launch = fuse ? kMaxGroup : 1;          // small shards: one scan launch per kMaxGroup queries
+    for (int g0 = 0; g0 < nq; g0 += per_launch) {
+        const int m = std::min(per_launch, nq - g0);
+        const uint8_t *dq[kMaxGroup];
+        Slot *sl[kMaxGroup];
+        cudaStream_t ss = next_scan_stream(ix);
+        for (int j = 0; j < m; ++j) {
+            Slot *slot = &ix->slot[first_slot + g0 + j];
+            const uint8_t *q = (const uint8_t *)queries + (size_t)(g0 + j) * (size_t)query_stride;
+            if (!query_on_device) {
+                if (slot->seq > 0) CU(cudaEventSynchronize(slot->done));   // the slot's pinned staging buffer is free again
+                rc = stage_query(ix, slot, q, ss);
+                if (rc) return rc;
+                q = slot->d_query;
+            }
+            dq[j] = q;
+            sl[j] = slot;
+        }
+        rc = launch_scan_group(ix, metric, dq, m, k, sl, nullptr, fetch != 0, ss, push);
+        if (rc) return rc;
+        ix->last_slot = first_slot + g0 + m - 1;
+        ix->last_metric = metric;
+    }
+    return VSB_OK;
+}
+
 }  // namespace
 
 #include "batch_host.inc"
+#include "exchange.inc"
 
 // ====================================================================== C ABI
 extern "C" {
@@ -658,6 +737,8 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "batch_m0")) p = &g_opt_batch_m0;
     else if (!strcmp(name, "batch_growth")) p = &g_opt_batch_growth;
     else if (!strcmp(name, "batch_debug")) p = &g_opt_batch_debug;
+    else if (!strcmp(name, "scan_streams")) p = &g_opt_scan_streams;
+    else if (!strcmp(name, "xwait_ms")) p = &g_opt_xwait_ms;
     if (!p) return fail(VSB_EINVAL, "unknown option %s", name);
     if (value < 0) return fail(VSB_EINVAL, "option %s: values are non-negative", name);   // so that a negative return is always an error
     int old = *p;
@@ -687,9 +768,13 @@ int vsb_index_create(vsb_index **out, int device, int vtype, int dim, int64_t ca
     ix->num_sms = pr.multiProcessorCount;
     ix->max_smem = (int)pr.sharedMemPerBlockOptin;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->fstream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->xstream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         if (ix->stream) cudaStreamDestroy(ix->stream);
+        if (ix->stream2) cudaStreamDestroy(ix->stream2);
+        if (ix->fstream) cudaStreamDestroy(ix->fstream);
         delete ix;
         return fail(VSB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
@@ -698,7 +783,9 @@ int vsb_index_create(vsb_index **out, int device, int vtype, int dim, int64_t ca
     if (e != cudaSuccess) {
         cudaGetLastError();
         cudaStreamDestroy(ix->stream);
+        cudaStreamDestroy(ix->stream2);
         cudaStreamDestroy(ix->fstream);
+        cudaStreamDestroy(ix->xstream);
         delete ix;
         return fail(VSB_ENOMEM, "cudaMalloc(%zu bytes) for the resident column failed: %s", bytes, cudaGetErrorString(e));
     }
@@ -842,7 +929,10 @@ void vsb_index_free(vsb_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
+    if (ix->stream2) cudaStreamSynchronize(ix->stream2);
     if (ix->fstream) cudaStreamSynchronize(ix->fstream);
+    if (ix->xstream) cudaStreamSynchronize(ix->xstream);
+    exchange_free(ix);
     for (int b = 0; b < 2; ++b) {
         if (ix->stage[b]) cudaFreeHost(ix->stage[b]);
         if (ix->stage_ev[b]) cudaEventDestroy(ix->stage_ev[b]);
@@ -866,6 +956,8 @@ void vsb_index_free(vsb_index *ix) {
     for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
     batch_free(ix);
     if (ix->fstream) cudaStreamDestroy(ix->fstream);
+    if (ix->xstream) cudaStreamDestroy(ix->xstream);
+    if (ix->stream2) cudaStreamDestroy(ix->stream2);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -915,7 +1007,7 @@ int vsb_scan_all(vsb_index *ix, int metric, const void *query, float *out_dist, 
     CU(cudaSetDevice(ix->device));
     int rc = ensure_slots(ix);
     if (rc) return rc;
-    rc = stage_query(ix, &ix->slot[0], query);
+    rc = stage_query(ix, &ix->slot[0], query, ix->stream);
     if (rc) return rc;
     std::vector<float> dist;
     rc = scan_all_into(ix, metric, ix->slot[0].d_query, dist);
@@ -968,6 +1060,7 @@ int vsb_debug_read(vsb_index *ix, const char *name, void *out, int64_t bytes) {
     if (!name || !out || bytes <= 0) return fail(VSB_EINVAL, "bad debug read arguments");
     CU(cudaSetDevice(ix->device));
     CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaStreamSynchronize(ix->stream2));
     CU(cudaStreamSynchronize(ix->fstream));
     const Work &w = ix->work[(ix->ws_next + kWorks - 1) % kWorks];     // the workspace of the most recent query
     const void *src = nullptr;
@@ -984,6 +1077,7 @@ int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches, double 
     if (check_index(ix)) return VSB_EINVAL;
     CU(cudaSetDevice(ix->device));
     CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaStreamSynchronize(ix->stream2));
     CU(cudaStreamSynchronize(ix->fstream));
     double a = 0, b = 0;
     int na = 0, nb = 0;
@@ -1018,14 +1112,15 @@ int vsb_scan_submit(vsb_index *ix, int metric, const void *query, int query_on_d
     const int si = want_slot >= 0 ? want_slot : (ix->last_slot + 1) % kSlots;
     Slot *slot = &ix->slot[si];
     const uint8_t *dq = (const uint8_t *)query;
+    cudaStream_t ss = next_scan_stream(ix);
     if (!query_on_device) {
         // the slot's pinned staging buffer is free once the slot's previous query has completed on the device
         if (slot->seq > 0) CU(cudaEventSynchronize(slot->done));
-        rc = stage_query(ix, slot, query);
+        rc = stage_query(ix, slot, query, ss);
         if (rc) return rc;
         dq = slot->d_query;
     }
-    rc = launch_scan(ix, metric, dq, k, slot, nullptr, fetch != 0);
+    rc = launch_scan(ix, metric, dq, k, slot, nullptr, fetch != 0, ss);
     if (rc) return rc;
     ix->last_slot = si;
     ix->last_metric = metric;
@@ -1034,38 +1129,7 @@ int vsb_scan_submit(vsb_index *ix, int metric, const void *query, int query_on_d
 
 int vsb_scan_submit_group(vsb_index *ix, int metric, const void *queries, int64_t query_stride, int nq, int query_on_device, int k,
                           int fetch, int first_slot) {
-    if (check_index(ix)) return VSB_EINVAL;
-    if (!queries || k <= 0 || k > kMaxK) return fail(VSB_EINVAL, "bad scan arguments (k must be 1..%d)", kMaxK);
-    if (nq <= 0 || first_slot < 0 || first_slot + nq > kSlots) return fail(VSB_EINVAL, "bad slot group [%d, %d)", first_slot, first_slot + nq);
-    CU(cudaSetDevice(ix->device));
-    int rc = ensure_slots(ix);
-    if (rc) return rc;
-    rc = ensure_workspace(ix, k);
-    if (rc) return rc;
-    const bool fuse = (double)ix->n * ix->pitch < (double)g_opt_fuse_mb * 1048576.0;
-    const int per_launch = fuse ? kMaxGroup : 1;          // small shards: one scan launch per kMaxGroup queries
-    for (int g0 = 0; g0 < nq; g0 += per_launch) {
-        const int m = std::min(per_launch, nq - g0);
-        const uint8_t *dq[kMaxGroup];
-        Slot *sl[kMaxGroup];
-        for (int j = 0; j < m; ++j) {
-            Slot *slot = &ix->slot[first_slot + g0 + j];
-            const uint8_t *q = (const uint8_t *)queries + (size_t)(g0 + j) * (size_t)query_stride;
-            if (!query_on_device) {
-                if (slot->seq > 0) CU(cudaEventSynchronize(slot->done));   // the slot's pinned staging buffer is free again
-                rc = stage_query(ix, slot, q);
-                if (rc) return rc;
-                q = slot->d_query;
-            }
-            dq[j] = q;
-            sl[j] = slot;
-        }
-        rc = launch_scan_group(ix, metric, dq, m, k, sl, nullptr, fetch != 0);
-        if (rc) return rc;
-        ix->last_slot = first_slot + g0 + m - 1;
-        ix->last_metric = metric;
-    }
-    return VSB_OK;
+    return submit_group(ix, metric, queries, query_stride, nq, query_on_device, k, fetch, first_slot, false);
 }
 
 int vsb_scan_device_query(vsb_index *ix, int metric, const void *d_query, int k) {

@@ -656,9 +656,61 @@ struct FilterQuery {    // per-query pointers of a (group) launch: blockIdx.y se
     int *hdr;           // hdr[0] = total survivors, hdr[1] = overflow flag, hdr[2] = sequence number
     int *ctrl;          // device: [0] cursor, [1] overflow from scan_kernel, [2] blocks done
     int seqno;
+    int xslot;          // push: slot row of the targets' gather buffers
+    unsigned xseq;      // push: exchange sequence number published with the head (hdr[4]) and raised on the flags
 };
 
+// NVLink peer-memory all-gather, fused into the filter: the block that completes a query's result head copies the used part
+// of it (header, block table, survivors) straight into the gather buffer of every target GPU — peer memory mapped through
+// cudaIpc (one process per GPU) or cudaDeviceEnablePeerAccess (one process, several GPUs) — and then raises that target's
+// arrival flag with a system-scope release store.  No NCCL kernel, no extra launch, no host synchronisation: the receiving
+// side waits on the flags with exchange_wait_kernel on ITS stream and copies the gathered heads to the host.
+constexpr int kMaxPeers = 16;
+struct PushParams {
+    int ntargets;                 // 0: nothing is pushed (single shard)
+    int src;                      // this shard's index inside a slot's gather row
+    int world;                    // shards per slot in the gather layout [slots][world][head_bytes]
+    int head_bytes, res_hdr_bytes;// layout of a head: [hdr 64 B][table][survivors from res_hdr_bytes on]
+    uint8_t *gather[kMaxPeers];   // target t: base of its gather buffer
+    unsigned *flags[kMaxPeers];   // target t: [slots][world] arrival flags (the exchange sequence number of the slot)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// receiving side: one thread per (slot of the group, source shard) spins until that shard's flag carries the expected
+// sequence number.  Bounded: after `timeout` clock cycles the missing head is marked (hdr[1] |= 8) so that the merge reports
+// an error instead of the GPU hanging on a peer that died.
+struct WaitParams {
+    const unsigned *flags;        // [slots][world]
+    uint8_t *gather;              // [slots][world][head_bytes] (local)
+    int world, first_slot, nq, head_bytes;
+    unsigned xseq[kMaxGroup];
+    long long timeout;
+};
+__global__ void exchange_wait_kernel(const WaitParams wp) {
+    const int t = threadIdx.x;
+    if (t >= wp.nq * wp.world) return;
+    const int j = t / wp.world, r = t % wp.world;
+    const size_t at = (size_t)(wp.first_slot + j) * wp.world + r;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(wp.flags + at) != wp.xseq[j]) {
+        if (clock64() - t0 > wp.timeout) {
+            reinterpret_cast<int *>(wp.gather + at * wp.head_bytes)[1] = 8;
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
 struct FilterParams {
+    PushParams push;
     int S;              // streams
     int k, kcap;
     int logcap;
@@ -887,18 +939,47 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
     }
     // last block publishes the header and re-arms the control words for the next query.  The host only reads the
     // mapped buffers after the stream has drained, so device-scope ordering between blocks is all that is needed.
+    __shared__ int is_last, push_total;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const int done = atomicAdd(&fq.ctrl[2], 1);
-        if (done == (int)gridDim.x - 1) {
+        const int last = (done == (int)gridDim.x - 1);
+        if (last) {
+            __threadfence();
             const int total = atomicAdd(&fq.ctrl[0], 0);
             const int ovf = atomicAdd(&fq.ctrl[1], 0);
             fq.hdr[0] = total;
             fq.hdr[1] = (ovf != 0 || total > fp.outcap) ? 1 : 0;
             fq.hdr[2] = fq.seqno;
             fq.hdr[3] = (int)gridDim.x;
+            fq.hdr[4] = (int)fq.xseq;
+            fq.hdr[5] = fp.push.src;
             fq.ctrl[0] = 0; fq.ctrl[1] = 0; fq.ctrl[2] = 0;
+            push_total = total;
+        }
+        is_last = last;
+    }
+    if (fp.push.ntargets > 0) {                                   // uniform across the grid
+        __syncthreads();
+        if (is_last) {
+            // the other blocks' survivors are visible: each fenced before its ctrl[2] increment, thread 0 fenced after
+            // observing the last one; read them through L2 (ld.cg), store them to peer memory over NVLink
+            const PushParams &pp = fp.push;
+            const int nhead = 8 + (int)gridDim.x;                                  // uint2 words of header + block table
+            const int nsurv = min(max(push_total, 0), fp.headcap);
+            const uint2 *src_head = reinterpret_cast<const uint2 *>(fq.hdr);
+            for (int t = 0; t < pp.ntargets; ++t) {
+                uint8_t *dst = pp.gather[t] + ((size_t)fq.xslot * pp.world + pp.src) * (size_t)pp.head_bytes;
+                uint2 *dh = reinterpret_cast<uint2 *>(dst);
+                uint2 *ds = reinterpret_cast<uint2 *>(dst + pp.res_hdr_bytes);
+                for (int i = (int)threadIdx.x; i < nhead; i += (int)blockDim.x) dh[i] = __ldcg(src_head + i);
+                for (int i = (int)threadIdx.x; i < nsurv; i += (int)blockDim.x) ds[i] = __ldcg(fq.out + i);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if ((int)threadIdx.x < pp.ntargets)
+                st_release_sys(pp.flags[threadIdx.x] + (size_t)fq.xslot * pp.world + pp.src, fq.xseq);
         }
     }
 }

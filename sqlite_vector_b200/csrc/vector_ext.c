@@ -8,8 +8,9 @@
  *                 vector_full_scan_stream, vector_quantize_scan_stream (tbl, col, vector)
  * Column state, option parsing, JSON vectors, quantization build and the shadow-table chunk format are host
  * C and behave like the reference (citations at each function).  What differs is where a scan runs:
- *   vector_quantize_preload  -> chunks are staged through pinned memory into HBM (vsb_index_append_quant_chunk)
- *   vector_quantize_scan     -> vsb_scan_topk on the resident shard (replaces vQuantRun/vQuantRunMemory, :2121-2236)
+ *   vector_quantize_preload  -> chunks are staged through pinned memory into HBM (vsb_group_append_quant_chunk), row-sharded
+ *                               over `gpus` GPUs (vector_init option gpus=N or env VSB_GPUS; default 1)
+ *   vector_quantize_scan     -> vsb_group_scan_topk on the resident shards (replaces vQuantRun/vQuantRunMemory, :2121-2236)
  *   vector_full_scan         -> the raw column is staged to HBM on first use and re-staged when the
  *                               connection's change counters move (replaces vFullScanRun, :2071-2113)
  * There is no CPU scan: without a CUDA device the scan functions fail with the engine's error text.
@@ -41,14 +42,15 @@ enum { COL_TBL = 0, COL_VECTOR = 1, COL_K = 2, COL_MEMIDX = 3, COL_ID = 4, COL_D
 typedef struct {
     char *tbl, *col, *pk;          /* pk: "rowid" or the INTEGER PRIMARY KEY of a WITHOUT ROWID table */
     int vtype, dim, normalized, metric, qtype;
+    int gpus;                      /* row shards (GPUs) the resident copies are spread over; option gpus=N / env VSB_GPUS, default 1 */
     uint64_t max_memory;
     float scale, offset;           /* quantization parameters (persisted in _sqliteai_vector) */
-    vsb_index *qix;                /* resident quantized shard */
+    vsb_group *qix;                /* resident quantized column: one shard per GPU (gpus = 1: a single shard) */
     int q_user_preloaded;          /* vector_quantize_preload was called (vs. staged lazily by a scan) */
     int q_tainted;                 /* lazily staged inside an open transaction: never reused (a ROLLBACK moves no counter) */
     sqlite3_int64 q_dataver;       /* PRAGMA data_version when the lazily staged copy was last verified */
     sqlite3_int64 q_fp[4];         /* shadow-table fingerprint at stage time: COUNT(*), SUM(counter), MIN(rowid1), MAX(rowid2) */
-    vsb_index *fix;                /* resident raw column for vector_full_scan */
+    vsb_group *fix;                /* resident raw column for vector_full_scan */
     sqlite3_int64 fix_dataver;
     int fix_changes;
     int fix_tainted;               /* staged inside an open transaction: never reused */
@@ -284,6 +286,7 @@ static char *single_int_pk(sqlite3 *db, const char *tbl) { /* :325-348 */
 /* ------------------------------------------------------------------------------------------------ options */
 typedef struct {
     int vtype, dim, normalized, metric, qtype;
+    int gpus;                      /* addition: 0 = not given */
     uint64_t max_memory;
 } voptions;
 
@@ -339,6 +342,12 @@ static int option_apply(sqlite3_context *ctx, voptions *o, const char *key, int 
         o->metric = m;
         return 1;
     }
+    if (!strncasecmp(key, "gpus", (size_t)klen)) {   /* addition (the reference ignores unknown keys, :990): row shards over N GPUs */
+        int g = !strcasecmp(buf, "all") ? vsb_device_count() : (int)strtol(buf, 0, 0);
+        if (g < 0) { fn_error(ctx, SQLITE_ERROR, "Invalid gpus value: expected a non-negative integer or 'all', got '%s'.", buf); return 0; }
+        o->gpus = g;
+        return 1;
+    }
     return 1; /* unknown keys are ignored (:990) */
 }
 
@@ -369,6 +378,20 @@ static int options_parse(sqlite3_context *ctx, const char *s, voptions *o) {
     return 1;
 }
 
+/* GPUs a column's resident copies are sharded over: option gpus=N, else env VSB_GPUS (N or "all"), else 1; never more than
+ * the devices that are visible (the same SQL runs on a 1-GPU box) */
+static int resolve_gpus(int opt) {
+    int g = opt;
+    if (g <= 0) {
+        const char *e = getenv("VSB_GPUS");
+        if (e && *e) g = !strcasecmp(e, "all") ? vsb_device_count() : atoi(e);
+    }
+    int have = vsb_device_count();
+    const char *alias = getenv("VSB_GROUP_ALIAS");      /* tests: more shards than GPUs (see vsb_group_create) */
+    if (g > have && !(alias && *alias && *alias != '0')) g = have;
+    return g < 1 ? 1 : g;
+}
+
 /* ------------------------------------------------------------------------------------------------ context */
 static vcolumn *ctx_find(vcontext *c, const char *tbl, const char *col) { /* vector_context_lookup, :1051-1061 */
     if (!tbl || !col) return 0;
@@ -379,8 +402,8 @@ static vcolumn *ctx_find(vcontext *c, const char *tbl, const char *col) { /* vec
     return 0;
 }
 static void column_drop_device(vcolumn *v) {
-    if (v->qix) { vsb_index_free(v->qix); v->qix = 0; }
-    if (v->fix) { vsb_index_free(v->fix); v->fix = 0; }
+    if (v->qix) { vsb_group_free(v->qix); v->qix = 0; }
+    if (v->fix) { vsb_group_free(v->fix); v->fix = 0; }
     v->q_user_preloaded = 0;
 }
 static void ctx_free(void *p) { /* vector_context_free, :1038-1049 */
@@ -587,6 +610,7 @@ static void fn_init(sqlite3_context *ctx, int argc, sqlite3_value **argv) { /* v
             fn_error(ctx, SQLITE_ERROR, "Inconsistent normalization flag for '%s.%s': existing=%s, provided=%s.", tbl, col, v->normalized ? "true" : "false", o.normalized ? "true" : "false");
             return;
         }
+        if (o.gpus > 0 && o.gpus != v->gpus) { v->gpus = o.gpus; column_drop_device(v); }   /* re-sharded on the next preload / scan */
         return;
     }
     if (vc->ncols >= MAX_COLUMNS) { fn_error(ctx, SQLITE_ERROR, "Cannot add table: maximum number of allowed tables reached (%d).", MAX_COLUMNS); return; }
@@ -604,6 +628,7 @@ static void fn_init(sqlite3_context *ctx, int argc, sqlite3_value **argv) { /* v
     memset(v, 0, sizeof *v);
     v->tbl = t; v->col = c; v->pk = pk;
     v->vtype = o.vtype; v->dim = o.dim; v->normalized = o.normalized; v->metric = o.metric; v->qtype = o.qtype; v->max_memory = o.max_memory;
+    v->gpus = o.gpus;
     column_load_meta(db, v);
 }
 
@@ -734,14 +759,14 @@ static void quant_fingerprint(sqlite3 *db, const vcolumn *v, sqlite3_int64 fp[4]
 
 /* stage every shadow-table chunk into HBM (the GPU counterpart of the loop at :1382-1394) */
 static int stage_quantized(sqlite3 *db, vcolumn *v, char **errmsg) {
-    if (v->qix) { vsb_index_free(v->qix); v->qix = 0; }
+    if (v->qix) { vsb_group_free(v->qix); v->qix = 0; }
     v->q_tainted = !sqlite3_get_autocommit(db);
     v->q_dataver = query_int64(db, "PRAGMA data_version;");
     quant_fingerprint(db, v, v->q_fp);
     char *sql = sqlite3_mprintf("SELECT SUM(counter) FROM vector0_%q_%q;", v->tbl, v->col);
     sqlite3_int64 rows = sql ? query_int64(db, sql) : 0;
     sqlite3_free(sql);
-    int rc = vsb_index_create(&v->qix, 0, v->qtype == VSB_QUANT_U8 ? VSB_U8 : VSB_I8, v->dim, rows, 0);
+    int rc = vsb_group_create(&v->qix, 0, resolve_gpus(v->gpus), v->qtype == VSB_QUANT_U8 ? VSB_U8 : VSB_I8, v->dim, rows);
     if (rc != VSB_OK) { *errmsg = sqlite3_mprintf("%s", vsb_last_error()); return SQLITE_ERROR; }
     sql = sqlite3_mprintf("SELECT counter, data FROM vector0_%q_%q;", v->tbl, v->col);
     sqlite3_stmt *st = 0;
@@ -754,14 +779,14 @@ static int stage_quantized(sqlite3 *db, vcolumn *v, char **errmsg) {
         sqlite3_int64 n = sqlite3_column_int64(st, 0);
         const void *data = sqlite3_column_blob(st, 1);
         if ((sqlite3_int64)sqlite3_column_bytes(st, 1) < n * (8 + (sqlite3_int64)v->dim)) { src = SQLITE_ERROR; *errmsg = sqlite3_mprintf("corrupt quantization chunk"); break; }
-        rc = vsb_index_append_quant_chunk(v->qix, data, n);
+        rc = vsb_group_append_quant_chunk(v->qix, data, n);
         if (rc != VSB_OK) { src = SQLITE_ERROR; *errmsg = sqlite3_mprintf("%s", vsb_last_error()); break; }
     }
     sqlite3_finalize(st);
-    if (src == SQLITE_OK && vsb_index_finalize(v->qix) != VSB_OK) { src = SQLITE_ERROR; *errmsg = sqlite3_mprintf("%s", vsb_last_error()); }
+    if (src == SQLITE_OK && vsb_group_finalize(v->qix) != VSB_OK) { src = SQLITE_ERROR; *errmsg = sqlite3_mprintf("%s", vsb_last_error()); }
     if (src != SQLITE_OK) {
         if (!*errmsg) *errmsg = sqlite3_mprintf("%s", sqlite3_errmsg(db));
-        vsb_index_free(v->qix);
+        vsb_group_free(v->qix);
         v->qix = 0;
     }
     return src;
@@ -818,12 +843,14 @@ static int do_quantize(sqlite3_context *ctx, const char *tbl, const char *col, c
     {
         voptions o;
         o.vtype = v->vtype; o.dim = v->dim; o.normalized = v->normalized; o.metric = v->metric; o.qtype = v->qtype; o.max_memory = v->max_memory;
+        o.gpus = v->gpus;
         /* NOTE: like the reference (:1429), the options start from the column's CURRENT options, so a qtype chosen by an
          * earlier AUTO run sticks unless overridden */
         if (!options_parse(ctx, opts, &o)) {   /* the reference returns here with its transaction open (:1431); we undo the DROP */
             sqlite3_exec(db, "ROLLBACK TO vsb_quantize; RELEASE vsb_quantize;", 0, 0, 0);
             return SQLITE_ERROR;              /* options_parse has set the error message */
         }
+        v->gpus = o.gpus;
         rc = rebuild_quantization(ctx, v, o.qtype, o.max_memory, &counter);
     }
     if (rc != SQLITE_OK) goto fail;
@@ -834,12 +861,12 @@ static int do_quantize(sqlite3_context *ctx, const char *tbl, const char *col, c
     if (rc == SQLITE_OK) rc = meta_store(ctx, tbl, col, "qoffset", 0, 0, (double)v->offset);
     if (rc != SQLITE_OK) goto fail;
     *was_preloaded = v->q_user_preloaded;
-    if (v->qix) { vsb_index_free(v->qix); v->qix = 0; } /* the device copy is a cache of the shadow table */
+    if (v->qix) { vsb_group_free(v->qix); v->qix = 0; } /* the device copy is a cache of the shadow table */
     sqlite3_result_int64(ctx, (sqlite3_int64)counter);
     return SQLITE_OK;
 fail:
     sqlite3_exec(db, "ROLLBACK TO vsb_quantize; RELEASE vsb_quantize;", 0, 0, 0);
-    if (v->qix && !v->q_user_preloaded) { vsb_index_free(v->qix); v->qix = 0; }
+    if (v->qix && !v->q_user_preloaded) { vsb_group_free(v->qix); v->qix = 0; }
     sqlite3_result_error_code(ctx, rc);
     return rc;
 }
@@ -884,7 +911,7 @@ static void fn_quantize_cleanup(sqlite3_context *ctx, int argc, sqlite3_value **
     const char *col = (const char *)sqlite3_value_text(argv[1]);
     vcolumn *v = ctx_find((vcontext *)sqlite3_user_data(ctx), tbl, col);
     if (!v) return;
-    if (v->qix) { vsb_index_free(v->qix); v->qix = 0; }
+    if (v->qix) { vsb_group_free(v->qix); v->qix = 0; }
     v->q_user_preloaded = 0;
     char *sql = sqlite3_mprintf("DROP TABLE IF EXISTS vector0_%q_%q;", tbl, col);
     if (sql) sqlite3_exec(sqlite3_context_db_handle(ctx), sql, 0, 0, 0);
@@ -903,11 +930,11 @@ static int stage_full_column(scan_vtab *vt, vcolumn *v) {
      * autocommit mode holds committed rows only; it stays valid until a counter moves. */
     const int in_txn = !sqlite3_get_autocommit(db);
     if (v->fix && !v->fix_tainted && v->fix_dataver == dataver && v->fix_changes == changes) return SQLITE_OK;
-    if (v->fix) { vsb_index_free(v->fix); v->fix = 0; }
+    if (v->fix) { vsb_group_free(v->fix); v->fix = 0; }
     char *sql = sqlite3_mprintf("SELECT COUNT(*) FROM %q;", v->tbl);
     sqlite3_int64 total = sql ? query_int64(db, sql) : 0;
     sqlite3_free(sql);
-    if (vsb_index_create(&v->fix, 0, v->vtype, v->dim, total, 0) != VSB_OK) return vtab_error(&vt->base, "vector_full_scan: %s", vsb_last_error());
+    if (vsb_group_create(&v->fix, 0, resolve_gpus(v->gpus), v->vtype, v->dim, total) != VSB_OK) return vtab_error(&vt->base, "vector_full_scan: %s", vsb_last_error());
     sql = sqlite3_mprintf("SELECT %q, %q FROM %q;", v->pk, v->col, v->tbl);
     sqlite3_stmt *st = 0;
     int rc = sql ? sqlite3_prepare_v2(db, sql, -1, &st, 0) : SQLITE_NOMEM;
@@ -932,17 +959,17 @@ static int stage_full_column(scan_vtab *vt, vcolumn *v) {
         memcpy(rows + (size_t)nb * need, blob, need);
         ids[nb++] = sqlite3_column_int64(st, 0);
         if (nb == batch_rows) {
-            if (vsb_index_append_dense(v->fix, rows, (const int64_t *)ids, nb) != VSB_OK) { rc = vtab_error(&vt->base, "vector_full_scan: %s", vsb_last_error()); break; }
+            if (vsb_group_append_dense(v->fix, rows, (const int64_t *)ids, nb) != VSB_OK) { rc = vtab_error(&vt->base, "vector_full_scan: %s", vsb_last_error()); break; }
             nb = 0;
         }
     }
-    if (rc == SQLITE_OK && nb > 0 && vsb_index_append_dense(v->fix, rows, (const int64_t *)ids, nb) != VSB_OK) rc = vtab_error(&vt->base, "vector_full_scan: %s", vsb_last_error());
-    if (rc == SQLITE_OK && vsb_index_finalize(v->fix) != VSB_OK) rc = vtab_error(&vt->base, "vector_full_scan: %s", vsb_last_error());
+    if (rc == SQLITE_OK && nb > 0 && vsb_group_append_dense(v->fix, rows, (const int64_t *)ids, nb) != VSB_OK) rc = vtab_error(&vt->base, "vector_full_scan: %s", vsb_last_error());
+    if (rc == SQLITE_OK && vsb_group_finalize(v->fix) != VSB_OK) rc = vtab_error(&vt->base, "vector_full_scan: %s", vsb_last_error());
     sqlite3_finalize(st);
     sqlite3_free(rows);
     sqlite3_free(ids);
     if (rc != SQLITE_OK) {
-        if (v->fix) { vsb_index_free(v->fix); v->fix = 0; }
+        if (v->fix) { vsb_group_free(v->fix); v->fix = 0; }
         if (!vt->base.zErrMsg) vtab_error(&vt->base, "vector_full_scan: %s", sqlite3_errmsg(db));
         return SQLITE_ERROR;
     }
@@ -1029,7 +1056,7 @@ static int vt_column(sqlite3_vtab_cursor *cur, sqlite3_context *ctx, int col) { 
 static int vt_rowid(sqlite3_vtab_cursor *cur, sqlite3_int64 *out) { *out = cur_id((scan_cursor *)cur); return SQLITE_OK; }
 
 /* the resident shard a scan runs on: the quantized column (staged from the shadow table on first use) or the raw column */
-static int resident_index(scan_vtab *vt, vcolumn *v, const char *tbl, const char *col, const char *fname, int quantized, vsb_index **out) {
+static int resident_index(scan_vtab *vt, vcolumn *v, const char *tbl, const char *col, const char *fname, int quantized, vsb_group **out) {
     if (quantized) {
         char *name = sqlite3_mprintf("vector0_%s_%s", tbl, col);
         int exists = name && sys_exists(vt->db, name, "table");
@@ -1049,7 +1076,7 @@ static int resident_index(scan_vtab *vt, vcolumn *v, const char *tbl, const char
                     v->q_dataver = dv;
                 }
             }
-            if (stale) { vsb_index_free(v->qix); v->qix = 0; column_load_meta(vt->db, v); }
+            if (stale) { vsb_group_free(v->qix); v->qix = 0; column_load_meta(vt->db, v); }
         }
         if (!v->qix) { /* not preloaded: the reference streams the chunks from disk per query (:2186-2227); we stage them once */
             char *err = 0;
@@ -1101,7 +1128,7 @@ static int filter_common(sqlite3_vtab_cursor *cur, int argc, sqlite3_value **arg
         if (sqlite3_value_bytes(argv[2]) < need) return vtab_error(&vt->base, "%s: input vector has %d bytes, expected %d.", fname, sqlite3_value_bytes(argv[2]), need);
     }
     int rc = SQLITE_OK;
-    vsb_index *ix = 0;
+    vsb_group *ix = 0;
     uint8_t *qq = 0;
     rc = resident_index(vt, v, tbl, col, fname, quantized, &ix);
     if (rc != SQLITE_OK) goto out;
@@ -1113,12 +1140,12 @@ static int filter_common(sqlite3_vtab_cursor *cur, int argc, sqlite3_value **arg
     }
 
     if (streaming) {
-        sqlite3_int64 n = vsb_index_rows(ix);
+        sqlite3_int64 n = vsb_group_rows(ix);
         sqlite3_free(c->sdist); sqlite3_free(c->sids);
         c->sdist = (float *)sqlite3_malloc64((sqlite3_uint64)(n > 0 ? n : 1) * sizeof(float));
         c->sids = (sqlite3_int64 *)sqlite3_malloc64((sqlite3_uint64)(n > 0 ? n : 1) * sizeof(sqlite3_int64));
         if (!c->sdist || !c->sids) { rc = SQLITE_NOMEM; goto out; }
-        if (n > 0 && vsb_scan_all(ix, v->metric, query, c->sdist, (int64_t *)c->sids) != VSB_OK) { rc = vtab_error(&vt->base, "%s: %s", fname, vsb_last_error()); goto out; }
+        if (n > 0 && vsb_group_scan_all(ix, v->metric, query, c->sdist, (int64_t *)c->sids) != VSB_OK) { rc = vtab_error(&vt->base, "%s: %s", fname, vsb_last_error()); goto out; }
         c->sn = n;
         c->spos = -1;
         goto out;
@@ -1137,7 +1164,7 @@ static int filter_common(sqlite3_vtab_cursor *cur, int argc, sqlite3_value **arg
         c->row_index = 0;
         c->row_count = 0;
         int count = 0;
-        if (vsb_scan_topk(ix, v->metric, query, 1, k, (int64_t *)c->ids, c->dist, &count, &c->max_index) != VSB_OK) {
+        if (vsb_group_scan_topk(ix, v->metric, query, 1, k, (int64_t *)c->ids, c->dist, &count, &c->max_index) != VSB_OK) {
             rc = vtab_error(&vt->base, "%s: %s", fname, vsb_last_error());
             goto out;
         }
@@ -1230,7 +1257,7 @@ static int filter_batch(sqlite3_vtab_cursor *cur, int argc, sqlite3_value **argv
     }
     int rc = SQLITE_OK;
     uint8_t *qq = 0;
-    vsb_index *ix = 0;
+    vsb_group *ix = 0;
     if (bytes <= 0 || bytes % need != 0) {
         rc = vtab_error(&vt->base, "%s: input has %d bytes, expected a positive multiple of %d (dimension %d).", fname, bytes, need, v->dim);
         goto out;
@@ -1254,7 +1281,7 @@ static int filter_batch(sqlite3_vtab_cursor *cur, int argc, sqlite3_value **argv
         c->dist = (double *)sqlite3_malloc64((sqlite3_uint64)nq * (sqlite3_uint64)k * sizeof(double));
         c->bcounts = (int *)sqlite3_malloc64((sqlite3_uint64)nq * sizeof(int));
         if (!c->ids || !c->dist || !c->bcounts) { rc = SQLITE_NOMEM; goto out; }
-        if (vsb_scan_topk(ix, v->metric, queries, nq, k, (int64_t *)c->ids, c->dist, c->bcounts, 0) != VSB_OK) {
+        if (vsb_group_scan_topk(ix, v->metric, queries, nq, k, (int64_t *)c->ids, c->dist, c->bcounts, 0) != VSB_OK) {
             rc = vtab_error(&vt->base, "%s: %s", fname, vsb_last_error());
             goto out;
         }

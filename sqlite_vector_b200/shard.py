@@ -141,6 +141,49 @@ class DeviceExchange:
         return self.world * self.stride
 
 
+class PeerExchange:
+    """The sharded single-query path of round 2: no collective library on the data path.  Setup all-gathers one 64-byte
+    cudaIpc handle per rank (torch.distributed object gather: plumbing); afterwards every filter kernel stores its result
+    head straight into every peer's gather buffer over NVLink and the engine waits / copies / merges (vsb_exchange_*).
+    Same interface as DeviceExchange (submit_strided / finish); requires implicit rowids (rowid = global row + 1)."""
+
+    def __init__(self, ix, engine, world: int, rank: int, bounds, group: int = 8):
+        import torch.distributed as dist
+        self.ix, self.eng, self.world, self.rank = ix, engine, world, rank
+        self.first_seq = np.asarray(bounds[:world], dtype=np.int64)
+        nslots = ix.stat("slots")
+        self.group = max(1, min(group, 8, nslots // 4))
+        self.ngroups = nslots // self.group          # slot groups used round-robin; at most ngroups // 2 may be in flight
+        self.max_in_flight = self.ngroups // 2
+        mine = ix.exchange_export(world, rank)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        ix.exchange_attach(b"".join(handles))
+        dist.barrier()                               # every rank has mapped every buffer before the first push
+        self.next_group = 0
+        self.stride = ix.stat("fetch_bytes")
+
+    def submit_strided(self, metric: int, queries, stride: int, nq: int, k: int, on_device: bool = True):
+        if not 0 < nq <= self.group:
+            raise ValueError(f"a group holds 1..{self.group} queries")
+        gi = self.next_group
+        self.next_group = (gi + 1) % self.ngroups
+        self.ix.exchange_submit(metric, queries, stride, nq, k, on_device, gi * self.group)
+        return gi, nq, k
+
+    def finish(self, ticket):
+        gi, nq, k = ticket
+        return self.ix.exchange_collect(gi * self.group, nq, self.first_seq, k)
+
+    def query(self, metric: int, query, k: int, on_device: bool = True):
+        q = query if on_device else np.ascontiguousarray(query).reshape(1, -1)
+        return self.finish(self.submit_strided(metric, q, 0, 1, k, on_device))[0]
+
+    @property
+    def d2h_bytes_per_query(self) -> int:
+        return self.world * self.stride
+
+
 def sharded_batch_topk(ix, metric: int, queries: np.ndarray, k: int, bounds, device, implicit_rowids: bool = True, as_arrays: bool = False):
     """Batched queries over a row-sharded column (BASELINE config 4).  Every rank runs the tensor-core batch path over
     its shard (vsb_batch_shard_scan), the shards' entry-log blocks are all-gathered device-to-device (NCCL over NVLink)
@@ -151,7 +194,7 @@ def sharded_batch_topk(ix, metric: int, queries: np.ndarray, k: int, bounds, dev
     import torch
     import torch.distributed as dist
 
-    from .api import VsbError
+    from .api import ERANGE, VsbError
 
     world = dist.get_world_size()
     q2 = np.ascontiguousarray(queries).reshape(-1, queries.shape[-1])
@@ -160,7 +203,9 @@ def sharded_batch_topk(ix, metric: int, queries: np.ndarray, k: int, bounds, dev
     try:
         ptr, nbytes = ix.batch_shard_scan(metric, q2, k)
         bad = 0
-    except VsbError:
+    except VsbError as ex:
+        if ex.rc != ERANGE:      # only "the batch path does not apply / a capacity was exceeded" is a reason to fall back
+            raise
         bad = 1
     # a shard that cannot take the batch path must not leave the others waiting in the collective
     flag = torch.tensor([bad], dtype=torch.int32, device=device)
@@ -173,7 +218,9 @@ def sharded_batch_topk(ix, metric: int, queries: np.ndarray, k: int, bounds, dev
     torch.cuda.current_stream(device).synchronize()
     try:
         seq, d, counts = ix.batch_merge(gathered.data_ptr(), world, nbytes, np.asarray(bounds[:world], dtype=np.int64), nq, k)
-    except VsbError:
+    except VsbError as ex:
+        if ex.rc != ERANGE:
+            raise
         return None          # an entry log overflowed: the same verdict on every rank (same gathered data)
     if implicit_rowids:
         ids = seq + 1

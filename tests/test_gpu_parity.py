@@ -334,9 +334,11 @@ def test_special_values_through_the_batch_path(eng, oracle, vtype):
     ix = make_index(vtype, x)
     rowids = np.arange(1, n + 1, dtype=np.int64)
     for metric in (po.L2, po.COS, po.DOT):
-        b0 = ix.stat("batches")
+        b0, f0 = ix.stat("batches"), ix.stat("fallbacks")
         res = ix.scan_topk(metric, q, k)
-        assert ix.stat("batches") == b0 + 1
+        # a query that holds an infinity makes every row a candidate: the batch call may then hit a capacity and fall back to the
+        # per-query path (counted); either way the tensor-core entry point was taken and the results must be the oracle's
+        assert ix.stat("batches") == b0 + 1 or ix.stat("fallbacks") > f0
         for b in range(nq):
             want_ids, want_d = oracle.scan_dense(metric, vtype, q[b], x, rowids, k)
             got_ids, got_d = res[b]

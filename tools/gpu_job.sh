@@ -18,7 +18,7 @@ NCU="ncu --clock-control none"
 for step in "$@"; do
   echo "=== [$TAG] $step  ($(date +%T))"
   case "$step" in
-    tests)      timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee ${O}_tests.txt ;;
+    tests)      timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -40 | tee ${O}_tests.txt ;;
     tests:*)    timeout 1500 python -m pytest tests -x -q -m gpu -k "${step#tests:}" 2>&1 | tail -15 | tee ${O}_tests_k.txt ;;
     bench)      timeout 900 python bench.py > ${O}_bench_n1.json 2> ${O}_bench_n1.err; tail -3 ${O}_bench_n1.err; python tools/bench_summary.py ${O}_bench_n1.json ;;
     bench_ref)  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > ${O}_bench_reference.json 2> ${O}_bench_reference.err; cut -c1-400 ${O}_bench_reference.json ;;

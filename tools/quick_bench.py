@@ -75,7 +75,7 @@ def main():
         e1.synchronize()
         ms = e0.elapsed_time(e1) / a.iters
         t0 = time.perf_counter()
-        qh = qv.cpu().numpy()
+        qh = qv.view(torch.int16).cpu().numpy().view(np.uint16) if a.vtype in (api.F16, api.BF16) else qv.cpu().numpy()
         for _ in range(a.iters):
             ix.scan_topk(a.metric, qh, a.k)
         e2e = (time.perf_counter() - t0) / a.iters * 1e3
