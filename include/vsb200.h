@@ -61,6 +61,15 @@ VSB_API const char *vsb_backend_name(void);
 /* capacity_rows is an upper bound on rows appended later; first_seq is the global scan-order index
  * of this shard's first row (0 on a single GPU). */
 VSB_API int vsb_index_create(vsb_index **out, int device, int vtype, int dim, int64_t capacity_rows, int64_t first_seq);
+/* corpora larger than the device budget (the role of the reference's not-preloaded path, src/sqlite-vector.c:2186-2227, which
+ * re-reads the chunks from the shadow table for every query): the column is kept in PINNED HOST memory and streamed through two
+ * device windows of window_rows rows each — the copy of window w+1 (cudaMemcpyAsync on its own stream) overlaps the scan of
+ * window w; every window is scanned like a shard and the survivors are replayed in scan order, so results are those of a
+ * resident index.  vsb_scan_topk / vsb_scan_all / vsb_scan_candidates work; the asynchronous, exchange and tensor-core batch entry
+ * points need a resident index.  Counters: vsb_index_stat "stream_bytes" / "stream_us". */
+VSB_API int vsb_index_create_streamed(vsb_index **out, int device, int vtype, int dim, int64_t capacity_rows, int64_t first_seq,
+                                      int64_t window_rows);
+VSB_API int vsb_index_is_streamed(const vsb_index *ix);
 /* rows x dim elements, row-major, HOST memory; rowids NULL => rowid = first_seq + row + 1.
  * Staged through pinned memory and copied with cudaMemcpyAsync. */
 VSB_API int vsb_index_append_dense(vsb_index *ix, const void *vectors, const int64_t *rowids, int64_t nrows);
@@ -194,8 +203,25 @@ VSB_API int64_t vsb_group_rows(const vsb_group *g);
 VSB_API vsb_index *vsb_group_shard(vsb_group *g, int shard); /* borrowed; for statistics */
 VSB_API void vsb_group_free(vsb_group *g);
 
+/* ---- GPU side of vector_quantize: replaces the two arithmetic loops of vector_rebuild_quantization (src/sqlite-vector.c:1224-1256
+ * min / max / "negative seen"; :1281-1320 quantize into chunks) with kernels; stepping through the table and writing the
+ * shadow-table rows stay with the extension.  Output bytes are identical to quantize_* / q_round_* (:495-757) and to the chunk
+ * layout [int64 LE rowid][dim x 8-bit] (:1295-1311).
+ * pass 1: vsb_quantizer_minmax for every block of rows (dense, source element type), then vsb_quantizer_minmax_result.
+ * pass 2: vsb_quantizer_encode per chunk.  With retain_rows > 0 pass 1 keeps the raw column in HBM when it fits (check
+ * vsb_quantizer_retained_rows() == rows fed), and pass 2 can encode rows [retained_first_row, +nrows) from there (rows == NULL):
+ * the table is then stepped once instead of twice. */
+typedef struct vsb_quantizer vsb_quantizer;
+VSB_API int vsb_quantizer_create(vsb_quantizer **out, int device, int src_vtype, int dim, int64_t retain_rows);
+VSB_API int vsb_quantizer_minmax(vsb_quantizer *qz, const void *rows, int64_t nrows);
+VSB_API int vsb_quantizer_minmax_result(vsb_quantizer *qz, float *lo, float *hi, int *negative);
+VSB_API int64_t vsb_quantizer_retained_rows(const vsb_quantizer *qz); /* rows kept in HBM by pass 1, or -1 when nothing is retained */
+VSB_API int vsb_quantizer_encode(vsb_quantizer *qz, const void *rows, int64_t retained_first_row, const int64_t *rowids, int64_t nrows,
+                                 float offset, float scale, int qtype, void *out_chunk /* nrows * (8 + dim) bytes, host */);
+VSB_API void vsb_quantizer_free(vsb_quantizer *qz);
+
 VSB_API int vsb_index_query_pitch(const vsb_index *ix); /* bytes per query row on the device (multiple of 16) */
-/* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes","slots","batches","batch_cands","batch_kept","tc_us","tc_rows","batch_us"}; -1 if unknown */
+/* counters since creation; name in {"queries","survivors","last_survivors","fallbacks","filter_blocks","fetch_bytes","slots","batches","batch_cands","batch_kept","tc_us","tc_rows","batch_us","stream_bytes","stream_us"}; -1 if unknown */
 VSB_API int64_t vsb_index_stat(const vsb_index *ix, const char *name);
 VSB_API void *vsb_index_stream(vsb_index *ix);           /* cudaStream_t of the engine, for event timing */
 /* kernel launch counter (all kernels launched by this library since load) */
@@ -206,7 +232,7 @@ VSB_API int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches,
 /* diagnostics: copies an internal device buffer of the most recent single-query scan to `out`; name in {"cta_time" (unsigned
  * cycles per scan CTA), "bounds" (int64 tile boundaries of the adaptive row partition)}.  Returns the bytes copied or < 0. */
 VSB_API int vsb_debug_read(vsb_index *ix, const char *name, void *out, int64_t bytes);
-/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat","epi2","batch_debug","batch_m0","batch_growth","balance","fuse_mb","scan_streams","xwait_ms","epi_max" (experimental),"tc_n" (experimental)};
+/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","bstat","epi2","batch_debug","batch_m0","batch_growth","balance","fuse_mb","scan_streams","xwait_ms","epi_chunk"};
  * values are non-negative; returns the previous value, or a negative VSB_E* code (unknown name, negative value) */
 VSB_API int vsb_set_option(const char *name, int value);
 

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "vsb_last_error": (C.c_char_p, []),
     "vsb_backend_name": (C.c_char_p, []),
     "vsb_index_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i64, _i64]),
+    "vsb_index_create_streamed": (_i, [C.POINTER(_vp), _i, _i, _i, _i64, _i64, _i64]),
+    "vsb_index_is_streamed": (_i, [_vp]),
     "vsb_index_append_dense": (_i, [_vp, _vp, _vp, _i64]),
     "vsb_index_append_quant_chunk": (_i, [_vp, _vp, _i64]),
     "vsb_index_append_device": (_i, [_vp, _vp, _vp, _i64]),
@@ -74,6 +76,12 @@ _SIGNATURES = {
     "vsb_group_rows": (_i64, [_vp]),
     "vsb_group_shard": (_vp, [_vp, _i]),
     "vsb_group_free": (None, [_vp]),
+    "vsb_quantizer_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i64]),
+    "vsb_quantizer_minmax": (_i, [_vp, _vp, _i64]),
+    "vsb_quantizer_minmax_result": (_i, [_vp, _vp, _vp, _vp]),
+    "vsb_quantizer_retained_rows": (_i64, [_vp]),
+    "vsb_quantizer_encode": (_i, [_vp, _vp, _i64, _vp, _i64, C.c_float, C.c_float, _i, _vp]),
+    "vsb_quantizer_free": (None, [_vp]),
     "vsb_index_query_pitch": (_i, [_vp]),
     "vsb_index_stream": (_vp, [_vp]),
     "vsb_index_stat": (_i64, [_vp, C.c_char_p]),
@@ -162,11 +170,16 @@ def load_engine() -> Engine:
 class Index:
     """A resident shard of one column on one GPU (table_context.preloaded on the device)."""
 
-    def __init__(self, vtype: int, dim: int, capacity: int, device: int = 0, first_seq: int = 0, engine: Engine | None = None):
+    def __init__(self, vtype: int, dim: int, capacity: int, device: int = 0, first_seq: int = 0, engine: Engine | None = None,
+                 window_rows: int = 0):
+        """window_rows > 0: streamed index (column in pinned host memory, two device windows of that many rows)"""
         self.eng = engine or load_engine()
         self.vtype, self.dim, self.device = vtype, dim, device
         h = _vp()
-        self.eng.check(self.eng.lib.vsb_index_create(C.byref(h), device, vtype, dim, capacity, first_seq))
+        if window_rows > 0:
+            self.eng.check(self.eng.lib.vsb_index_create_streamed(C.byref(h), device, vtype, dim, capacity, first_seq, window_rows))
+        else:
+            self.eng.check(self.eng.lib.vsb_index_create(C.byref(h), device, vtype, dim, capacity, first_seq))
         self.h = h
 
     def close(self):
@@ -390,3 +403,42 @@ class Group:
         ids = np.zeros(n, dtype=np.int64) if want_rowids else None
         self.eng.check(self.eng.lib.vsb_group_scan_all(self.h, metric, _ptr(np.ascontiguousarray(query)), _ptr(dist), _ptr(ids)))
         return (dist, ids) if want_rowids else dist
+
+
+class Quantizer:
+    """GPU side of vector_quantize (vsb_quantizer_*): min / max pass and chunk encoding, byte-identical to the reference."""
+
+    def __init__(self, src_vtype: int, dim: int, retain_rows: int = 0, device: int = 0, engine: Engine | None = None):
+        self.eng = engine or load_engine()
+        self.vtype, self.dim = src_vtype, dim
+        h = _vp()
+        self.eng.check(self.eng.lib.vsb_quantizer_create(C.byref(h), device, src_vtype, dim, retain_rows))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.eng.lib.vsb_quantizer_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def minmax(self, rows: np.ndarray):
+        self.eng.check(self.eng.lib.vsb_quantizer_minmax(self.h, _ptr(np.ascontiguousarray(rows)), rows.shape[0]))
+
+    def minmax_result(self):
+        lo, hi, neg = C.c_float(), C.c_float(), C.c_int()
+        self.eng.check(self.eng.lib.vsb_quantizer_minmax_result(self.h, C.byref(lo), C.byref(hi), C.byref(neg)))
+        return lo.value, hi.value, bool(neg.value)
+
+    @property
+    def retained_rows(self) -> int:
+        return int(self.eng.lib.vsb_quantizer_retained_rows(self.h))
+
+    def encode(self, rows, rowids: np.ndarray, offset: float, scale: float, qtype: int, retained_first_row: int = 0) -> np.ndarray:
+        """rows: host array, or None to encode rows [retained_first_row, +len(rowids)) kept in HBM by minmax"""
+        rid = np.ascontiguousarray(rowids, dtype=np.int64)
+        n = rid.shape[0]
+        out = np.zeros(n * (8 + self.dim), dtype=np.uint8)
+        ptr = None if rows is None else _ptr(np.ascontiguousarray(rows))
+        self.eng.check(self.eng.lib.vsb_quantizer_encode(self.h, ptr, retained_first_row, _ptr(rid), n, C.c_float(offset), C.c_float(scale), qtype, _ptr(out)))
+        return out

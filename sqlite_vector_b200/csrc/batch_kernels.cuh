@@ -178,16 +178,17 @@ struct TileIter {
 };
 
 // CH: accumulator columns per epilogue step (64 = two 32-column TMEM loads in flight per buffer, 32 = one)
-// TEST: 0 = every score is compared with its query's bound (IADD3 + predicate-chained ISETP per score);
-//       1 = EXPERIMENTAL, not yet run on a GPU (option "epi_max", off by default): integer kinds, L2 / DOT, CH = 32: a running
-//           maximum of (2 s_j - qc_j) resp. (s_j - qc_j) over the 32 columns and ONE comparison against the row constant
-//           (a hit exists in the chunk iff the maximum passes); the exact per-column masks are only computed for chunks
-//           that have a hit, as before.
-// NACC: accumulator buffers in TMEM (NACC * N <= 512 columns).  2 is the validated configuration; 4 (with N = 128) is
-//       EXPERIMENTAL like TEST = 1 (option "tc_n" = 128): the MMA may run three tiles ahead of the epilogue.
-template <int KIND, int MC, bool BSTAT, int EPI, int CH, int TEST = 0, int NACC = 2>
+// TEST: 0 = every score is compared with its query's bound (two dependent ALU ops per score: at K = 384 bytes the epilogue,
+//           not the MMA, set the tile time: tensor pipe 49 %, profiles/r01e_ncu_summary.json);
+//       2 = chunk test (integer kinds, CH = 32; the default): the hit condition is monotone in the score, so a 32-column chunk
+//           can only contain a hit if  max_j s_ij  passes against the chunk's WEAKEST bound  min_j qc_j  (precomputed per chunk
+//           in shared memory).  The maximum costs 16 three-input VIMNMX per 32 scores instead of 64 dependent IADD3/ISETP, no
+//           per-column constants are loaded, and only chunks that pass (a few in 10^4 for queries of similar norm) run the
+//           per-column test that builds the exact hit masks.  The log is the same set of (row, query) pairs either way.
+template <int KIND, int MC, bool BSTAT, int EPI, int CH, int TEST = 0>
 __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, const TcParams prm) {
+    constexpr int NACC = 2;                                                    // accumulator buffers in TMEM (2 x N <= 512 columns)
     constexpr bool INT8 = (KIND == TK_I8 || KIND == TK_U8);
     extern __shared__ __align__(1024) uint8_t tsm[];
     const int N = prm.N, NS = prm.nstages;
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
     uint64_t *bempty = bfull + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bempty + 1);
     uint32_t *qc_s = tmem_slot + 4;                                            // [NG*N]
+    uint32_t *qcm_s = qc_s + prm.NG * prm.N;                                   // [NG*N/32] weakest bound of each 32-column chunk (TEST = 2)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_cols = (NACC * N <= 32) ? 32 : (NACC * N <= 64 ? 64 : (NACC * N <= 128 ? 128 : (NACC * N <= 256 ? 256 : 512)));
@@ -216,18 +218,25 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
-    constexpr bool kMaxTest = (TEST == 1) && INT8 && (MC == MC_L2 || MC == MC_DOT) && CH == 32;
-    for (int i = threadIdx.x; i < prm.NG * N; i += tc_threads(EPI)) {
-        uint32_t c = __float_as_uint(prm.qc[i]);
-        if constexpr (kMaxTest) {
-            // keep (2 s - qc) inside int32: bounds beyond +-2^30 mean "always" / "never" for every reachable score anyway
-            c = (uint32_t)max(-(1 << 30), min(1 << 30, (int)c));
-        }
-        qc_s[i] = c;
-    }
+    constexpr bool kChunkTest = (TEST == 2) && INT8 && CH == 32;
+    for (int i = threadIdx.x; i < prm.NG * N; i += tc_threads(EPI)) qc_s[i] = __float_as_uint(prm.qc[i]);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if constexpr (kChunkTest) {
+        for (int c = threadIdx.x; c < prm.NG * N / 32; c += tc_threads(EPI)) {
+            if constexpr (MC == MC_COS) {
+                float m = __uint_as_float(qc_s[c * 32]);
+                for (int j = 1; j < 32; ++j) m = fminf(m, __uint_as_float(qc_s[c * 32 + j]));
+                qcm_s[c] = __float_as_uint(m);
+            } else {
+                int m = (int)qc_s[c * 32];
+                for (int j = 1; j < 32; ++j) m = min(m, (int)qc_s[c * 32 + j]);
+                qcm_s[c] = (uint32_t)m;
+            }
+        }
+        __syncthreads();
+    }
     const uint32_t tmem_base = *tmem_slot;
 
     TileIter ti;
@@ -337,24 +346,20 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
                 const uint4 *qc4 = reinterpret_cast<const uint4 *>(qc_s + ng * N + cb);
                 constexpr int C0 = CH < 32 ? CH : 32;                          // columns in the first 32-column half
                 bool any0 = false, any1 = false;
-                if constexpr (kMaxTest) {
-                    int m0 = INT_MIN, m1 = INT_MIN;
+                if constexpr (kChunkTest) {
+                    int m0 = INT_MIN, m1 = INT_MIN, m2 = INT_MIN, m3 = INT_MIN;   // four independent chains of 3-input maxima
 #pragma unroll
-                    for (int j4 = 0; j4 < C0 / 4; ++j4) {
-                        const uint4 c = qc4[j4];
-                        int a, b, e, f;
-                        if constexpr (MC == MC_L2) {
-                            a = 2 * (int)v[4 * j4 + 0] - (int)c.x; b = 2 * (int)v[4 * j4 + 1] - (int)c.y;
-                            e = 2 * (int)v[4 * j4 + 2] - (int)c.z; f = 2 * (int)v[4 * j4 + 3] - (int)c.w;
-                        } else {
-                            a = (int)v[4 * j4 + 0] - (int)c.x; b = (int)v[4 * j4 + 1] - (int)c.y;
-                            e = (int)v[4 * j4 + 2] - (int)c.z; f = (int)v[4 * j4 + 3] - (int)c.w;
-                        }
-                        m0 = max(m0, max(a, b));
-                        m1 = max(m1, max(e, f));
+                    for (int j = 0; j < 32; j += 8) {
+                        m0 = max(m0, max((int)v[j + 0], (int)v[j + 1]));
+                        m1 = max(m1, max((int)v[j + 2], (int)v[j + 3]));
+                        m2 = max(m2, max((int)v[j + 4], (int)v[j + 5]));
+                        m3 = max(m3, max((int)v[j + 6], (int)v[j + 7]));
                     }
-                    const int m = max(m0, m1);
-                    any0 = (MC == MC_L2) ? (m >= -rowi) : (m > 0);          // rowi = -|row|^2:  2 s + rowi >= qc  <=>  2 s - qc >= -rowi
+                    const int m = max(max(m0, m1), max(m2, m3));
+                    const uint32_t qm = qcm_s[(ng * N + cb) >> 5];
+                    if constexpr (MC == MC_DOT) any0 = m > (int)qm;
+                    else if constexpr (MC == MC_L2) any0 = (2 * m + rowi) >= (int)qm;
+                    else any0 = !(fmaf(-__uint_as_float(qm), rowf, (float)m) < 0.0f);   // rowf >= 0: monotone in both m and the bound
                 } else {
 #pragma unroll
                     for (int j4 = 0; j4 < C0 / 4; ++j4) {

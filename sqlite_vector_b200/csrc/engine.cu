@@ -20,10 +20,12 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "scan_kernels.cuh"
 #include "batch_kernels.cuh"
+#include "quant_kernels.cuh"
 
 using namespace vsb;
 
@@ -44,8 +46,7 @@ int g_opt_fuse_mb = 0;         // > 0: vsb_scan_submit_group fuses a group into 
                                // Off by default: a persistent 8-query launch leaves the NCCL all-gather of the previous group no SM until
                                // it ends (2 GPUs: the step-vs-scan gap grew from 3 to 14 us per query), not yet measured at 8 GPUs.
 int g_opt_balance = 1;         // 1: adaptive row partition of the single-query scan (per-CTA speeds feed the next partition)
-int g_opt_tc_n = 0;            // 128: EXPERIMENTAL 128-query tensor-core tiles with four TMEM accumulator buffers (not validated on a GPU yet)
-int g_opt_epi_max = 0;         // 1: EXPERIMENTAL running-maximum pre-test in the int8/uint8 L2 / DOT tensor-core epilogue (not validated on a GPU yet)
+int g_opt_epi_chunk = 1;       // 1: integer tensor-core epilogue tests 32-column chunks (max score vs weakest bound) before any per-column work
 int g_opt_epi2 = 2;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 2 = 8 epilogue warps, two per TMEM lane quadrant
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
 int g_opt_scan_streams = 2;    // 2: consecutive scan launches alternate between two streams, so the CTAs of launch i+1 take over each SM
@@ -165,6 +166,15 @@ struct vsb_index {
     int stage_next = 0;
     int num_sms = 0, max_smem = 0;
     cudaStream_t fstream = nullptr;   // filter + result copy of a query; `stream` carries staging, scans and the batch path
+    // streamed mode (corpus larger than the device budget): the column lives in pinned host memory and passes
+    // through two device windows of win_rows rows; every window is scanned like a shard while the next one is copied
+    bool streamed = false;
+    uint8_t *h_arena = nullptr;       // [cap][pitch] pinned
+    uint8_t *d_win[2] = {nullptr, nullptr};
+    long long win_rows = 0;
+    cudaStream_t cstream = nullptr;   // window copies
+    cudaEvent_t win_copied[2] = {nullptr, nullptr}, win_scanned[2] = {nullptr, nullptr};
+    long long st_stream_bytes = 0, st_stream_us = 0;
     cudaStream_t stream2 = nullptr;   // second scan stream (option scan_streams = 2): single-query scans alternate between the two
     cudaStream_t xstream = nullptr;   // exchange: flag wait + copy of the gathered heads to the host
     int snext = 0;
@@ -366,8 +376,12 @@ int exchange_fill_push(vsb_index *ix, PushParams *pp);
 // one filter launch (grid.y = nq) on ix->fstream.  slots[g] receives query g's result.
 // fetch: copy the slots' heads to pinned host memory afterwards (false when the heads are all-gathered on the device)
 // ss: the scan stream of this launch (next_scan_stream); push: the filter also pushes each head into the exchange targets
+// view_vec / view_n: scan these rows instead of the resident column (the windows of a streamed index)
 int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries, int nq, int k, Slot *const *slots, float *d_dist_all,
-                      bool fetch, cudaStream_t ss, bool push = false) {
+                      bool fetch, cudaStream_t ss, bool push = false, const uint8_t *view_vec = nullptr, long long view_n = -1) {
+    const uint8_t *scan_vec = view_vec ? view_vec : ix->d_vec;
+    const long long scan_n = view_vec ? view_n : ix->n;
+    if (!scan_vec) return fail(VSB_EINVAL, "this entry point needs a resident (not streamed) index");
     int root = 0;
     const int mc = metric_class(metric, &root);
     if (mc < 0) return fail(VSB_EINVAL, "unknown distance metric %d", metric);
@@ -394,7 +408,7 @@ int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries
     }
     // adaptive partition (k <= 32 path only: that filter kernel maintains it): equal shares to start with
     const long long rpw = 32 >> pl.log2P;
-    const long long total_tiles = (ix->n + rpw - 1) / rpw;
+    const long long total_tiles = (scan_n + rpw - 1) / rpw;
     const bool balance = wk != nullptr && g_opt_balance && kcap == 32 && total_tiles >= 64ll * ix->num_sms;
     if (balance && wk->bounds_tiles != total_tiles) {
         std::vector<long long> b((size_t)ix->num_sms + 1);
@@ -404,8 +418,8 @@ int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries
         wk->bounds_tiles = total_tiles;
     }
     ScanParams p{};
-    p.vec = ix->d_vec;
-    p.n = ix->n;
+    p.vec = scan_vec;
+    p.n = scan_n;
     p.pitch = ix->pitch;
     p.nc = ix->pitch / 16;
     p.log2P = pl.log2P;
@@ -591,7 +605,13 @@ int gather_survivors(vsb_index *ix, Slot *slot, std::vector<uint2> &out, bool *o
     return (int)out.size();
 }
 
+int streamed_scan_all(vsb_index *ix, int metric, const uint8_t *d_query, float *out_dist);
+
 int scan_all_into(vsb_index *ix, int metric, const uint8_t *d_query, std::vector<float> &dist) {
+    if (ix->streamed) {
+        dist.resize((size_t)ix->n);
+        return streamed_scan_all(ix, metric, d_query, dist.data());
+    }
     if (!ix->d_dist_all) {
         CU(cudaMalloc((void **)&ix->d_dist_all, sizeof(float) * (size_t)std::max<long long>(ix->cap, 1)));
         ix->dev_bytes += sizeof(float) * (size_t)ix->cap;
@@ -612,16 +632,111 @@ int stage_query(vsb_index *ix, Slot *slot, const void *query, cudaStream_t ss) {
     return VSB_OK;
 }
 
+// ---- streamed index: the window loop.  Window w (rows [w * win_rows, ...)) is copied into d_win[w & 1] on the copy stream
+// while window w-1 is being scanned; a window is scanned exactly like a shard (scan + filter into a result slot), its survivors
+// carry window-local rows.  visit(w, first_row, rows, slot) is called in window order once the slot's head is on the host.
+template <class Launch, class Visit>
+int stream_windows(vsb_index *ix, int depth, Launch launch, Visit visit) {
+    const long long W = (ix->n + ix->win_rows - 1) / ix->win_rows;
+    const auto t0 = std::chrono::steady_clock::now();
+    long long next_visit = 0;
+    for (long long w = 0; w < W; ++w) {
+        const int b = (int)(w & 1);
+        const long long r0 = w * ix->win_rows, rows = std::min(ix->win_rows, ix->n - r0);
+        if (w >= 2) CU(cudaStreamWaitEvent(ix->cstream, ix->win_scanned[b], 0));       // the scan of window w-2 has read this buffer
+        CU(cudaMemcpyAsync(ix->d_win[b], ix->h_arena + (size_t)r0 * ix->pitch, (size_t)rows * ix->pitch, cudaMemcpyHostToDevice, ix->cstream));
+        CU(cudaEventRecord(ix->win_copied[b], ix->cstream));
+        CU(cudaStreamWaitEvent(ix->stream, ix->win_copied[b], 0));
+        while (w - next_visit >= depth) {                                                // free the slot this window will use
+            const int rc = visit(next_visit, next_visit * ix->win_rows, std::min(ix->win_rows, ix->n - next_visit * ix->win_rows), (int)(next_visit % depth));
+            if (rc) return rc;
+            ++next_visit;
+        }
+        const int rc = launch(w, ix->d_win[b], rows, (int)(w % depth));
+        if (rc) return rc;
+        CU(cudaEventRecord(ix->win_scanned[b], ix->stream));
+        ix->st_stream_bytes += rows * ix->pitch;
+    }
+    for (; next_visit < W; ++next_visit) {
+        const int rc = visit(next_visit, next_visit * ix->win_rows, std::min(ix->win_rows, ix->n - next_visit * ix->win_rows), (int)(next_visit % depth));
+        if (rc) return rc;
+    }
+    ix->st_stream_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    return VSB_OK;
+}
+
+// all distances of a streamed index (stream modules, k > 256, overflow fallback)
+int streamed_scan_all(vsb_index *ix, int metric, const uint8_t *d_query, float *out_dist) {
+    if (!ix->d_dist_all) {
+        CU(cudaMalloc((void **)&ix->d_dist_all, sizeof(float) * 2 * (size_t)ix->win_rows));
+        ix->dev_bytes += sizeof(float) * 2 * (size_t)ix->win_rows;
+    }
+    return stream_windows(ix, 2,
+        [&](long long, const uint8_t *vec, long long rows, int s) {
+            return launch_scan_group(ix, metric, &d_query, 1, 0, nullptr, ix->d_dist_all + (size_t)s * ix->win_rows, false, ix->stream, false, vec, rows);
+        },
+        [&](long long, long long r0, long long rows, int s) {
+            // distances of window w sit in half s of d_dist_all; the copy is ordered behind that window's scan on the same stream
+            CU(cudaMemcpyAsync(out_dist + r0, ix->d_dist_all + (size_t)s * ix->win_rows, sizeof(float) * (size_t)rows, cudaMemcpyDeviceToHost, ix->stream));
+            CU(cudaStreamSynchronize(ix->stream));
+            return (int)VSB_OK;
+        });
+}
+
+// candidates of a streamed index: every window's survivors, in scan order, rows made column-global
+int streamed_candidates(vsb_index *ix, int metric, const uint8_t *d_query, int k, std::vector<uint2> &cands, bool *overflow) {
+    cands.clear();
+    *overflow = false;
+    const int depth = 4;                                  // result slots 0..3 rotate over the windows
+    std::vector<uint2> part;
+    return stream_windows(ix, depth,
+        [&](long long, const uint8_t *vec, long long rows, int s) {
+            Slot *slot = &ix->slot[s];
+            return launch_scan_group(ix, metric, &d_query, 1, k, &slot, nullptr, true, ix->stream, false, vec, rows);
+        },
+        [&](long long, long long r0, long long, int s) {
+            Slot *slot = &ix->slot[s];
+            CU(cudaEventSynchronize(slot->done));
+            bool ovf = false;
+            const int n = gather_survivors(ix, slot, part, &ovf);
+            if (n < 0) return n;
+            if (ovf) *overflow = true;
+            for (const uint2 &c : part) cands.push_back(make_uint2(c.x, c.y + (uint32_t)r0));
+            return (int)VSB_OK;
+        });
+}
+
 // one query, host in / candidates out (sorted by scan order).  Falls back to the all-distances kernel when the
 // candidate log overflowed or k is larger than the candidate path supports (still GPU-computed distances).
 int query_candidates(vsb_index *ix, int metric, const void *query, int k, std::vector<uint2> &cands) {
     CU(cudaSetDevice(ix->device));
     int rc = ensure_slots(ix);
     if (rc) return rc;
-    Slot *slot = &ix->slot[0];
+    Slot *slot = &ix->slot[ix->streamed ? kSlots - 1 : 0];   // streamed: slots 0..3 rotate over the windows, the query is parked in the last one
     rc = stage_query(ix, slot, query, ix->stream);   // synchronous call: one stream (a possible all-distances fallback reads d_query on it)
     if (rc) return rc;
     bool overflow = (k > kMaxK);
+    if (ix->streamed) {
+        if (!overflow) {
+            rc = ensure_workspace(ix, k);
+            if (rc) return rc;
+            rc = streamed_candidates(ix, metric, slot->d_query, k, cands, &overflow);
+            if (rc) return rc;
+        }
+        if (overflow) {
+            ix->st_fallbacks++;
+            std::vector<float> dist;
+            rc = scan_all_into(ix, metric, slot->d_query, dist);
+            if (rc) return rc;
+            cands.resize((size_t)ix->n);
+            for (long long i = 0; i < ix->n; ++i) {
+                uint32_t bits;
+                memcpy(&bits, &dist[(size_t)i], 4);
+                cands[(size_t)i] = make_uint2(bits, (uint32_t)i);
+            }
+        }
+        return VSB_OK;
+    }
     if (!overflow) {
         rc = ensure_workspace(ix, k);
         if (rc) return rc;
@@ -694,6 +809,7 @@ int submit_group(vsb_index *ix, int metric, const void *queries, int64_t query_s
 
 #include "batch_host.inc"
 #include "exchange.inc"
+#include "quantize.inc"
 
 // ====================================================================== C ABI
 extern "C" {
@@ -730,8 +846,7 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "no_batch")) p = &g_opt_no_batch;
     else if (!strcmp(name, "bstat")) p = &g_opt_bstat;
     else if (!strcmp(name, "epi2")) p = &g_opt_epi2;
-    else if (!strcmp(name, "epi_max")) p = &g_opt_epi_max;
-    else if (!strcmp(name, "tc_n")) p = &g_opt_tc_n;
+    else if (!strcmp(name, "epi_chunk")) p = &g_opt_epi_chunk;
     else if (!strcmp(name, "balance")) p = &g_opt_balance;
     else if (!strcmp(name, "fuse_mb")) p = &g_opt_fuse_mb;
     else if (!strcmp(name, "batch_m0")) p = &g_opt_batch_m0;
@@ -746,7 +861,20 @@ int vsb_set_option(const char *name, int value) {
     return old;
 }
 
+static int index_create(vsb_index **out, int device, int vtype, int dim, int64_t capacity_rows, int64_t first_seq, int64_t window_rows);
+
 int vsb_index_create(vsb_index **out, int device, int vtype, int dim, int64_t capacity_rows, int64_t first_seq) {
+    return index_create(out, device, vtype, dim, capacity_rows, first_seq, 0);
+}
+
+int vsb_index_create_streamed(vsb_index **out, int device, int vtype, int dim, int64_t capacity_rows, int64_t first_seq, int64_t window_rows) {
+    if (window_rows <= 0) return fail(VSB_EINVAL, "window_rows must be positive");
+    return index_create(out, device, vtype, dim, capacity_rows, first_seq, window_rows);
+}
+
+int vsb_index_is_streamed(const vsb_index *ix) { return ix && ix->streamed ? 1 : 0; }
+
+static int index_create(vsb_index **out, int device, int vtype, int dim, int64_t capacity_rows, int64_t first_seq, int64_t window_rows) {
     if (!out) return fail(VSB_EINVAL, "out is null");
     *out = nullptr;
     const int es = elem_size(vtype);
@@ -778,16 +906,28 @@ int vsb_index_create(vsb_index **out, int device, int vtype, int dim, int64_t ca
         delete ix;
         return fail(VSB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
-    const size_t bytes = (size_t)std::max<long long>(capacity_rows, 1) * ix->pitch + 1024;
-    e = cudaMalloc((void **)&ix->d_vec, bytes);
+    size_t bytes = (size_t)std::max<long long>(capacity_rows, 1) * ix->pitch + 1024;
+    if (window_rows > 0) {
+        // streamed: the column stays in pinned host memory, two windows on the device
+        ix->streamed = true;
+        ix->win_rows = std::min<long long>(std::max<long long>(window_rows, 32), std::max<long long>(capacity_rows, 32));
+        e = cudaHostAlloc((void **)&ix->h_arena, bytes, cudaHostAllocDefault);
+        const size_t wb = (size_t)ix->win_rows * ix->pitch + 1024;
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+            e = cudaMalloc((void **)&ix->d_win[b], wb);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->win_copied[b], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->win_scanned[b], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->cstream, cudaStreamNonBlocking);
+        bytes = 2 * wb;
+    } else {
+        e = cudaMalloc((void **)&ix->d_vec, bytes);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
-        cudaStreamDestroy(ix->stream);
-        cudaStreamDestroy(ix->stream2);
-        cudaStreamDestroy(ix->fstream);
-        cudaStreamDestroy(ix->xstream);
-        delete ix;
-        return fail(VSB_ENOMEM, "cudaMalloc(%zu bytes) for the resident column failed: %s", bytes, cudaGetErrorString(e));
+        const std::string why = cudaGetErrorString(e);
+        vsb_index_free(ix);
+        return fail(VSB_ENOMEM, "allocating %zu bytes for the %s column failed: %s", bytes, window_rows > 0 ? "streamed" : "resident", why.c_str());
     }
     ix->dev_bytes = bytes;
     *out = ix;
@@ -825,6 +965,20 @@ static int append_rows(vsb_index *ix, const uint8_t *src, size_t src_stride, siz
     if (pitch > kStageBuf) return fail(VSB_ERANGE, "row pitch %zu exceeds the %zu-byte staging buffer", pitch, (size_t)kStageBuf);
     const int64_t per_buf = (int64_t)(kStageBuf / pitch);
     int64_t done = 0;
+    if (ix->streamed) {                      // the pinned arena IS the staging area
+        for (int64_t r = 0; r < nrows; ++r) {
+            const uint8_t *row = src + (size_t)r * src_stride;
+            uint8_t *dst = ix->h_arena + (size_t)(ix->n + r) * pitch;
+            memcpy(dst, row + src_off, rowbytes);
+            if (pitch > rowbytes) memset(dst + rowbytes, 0, pitch - rowbytes);
+            if (ids_inline) {
+                uint64_t v = 0;
+                for (int i = 7; i >= 0; --i) v = (v << 8) | row[i];
+                ix->h_rowids.push_back((int64_t)v);
+            }
+        }
+        done = nrows;
+    }
     while (done < nrows) {
         const int64_t m = std::min<int64_t>(per_buf, nrows - done);
         int b;
@@ -870,6 +1024,7 @@ int vsb_index_append_quant_chunk(vsb_index *ix, const void *chunk, int64_t nrows
 int vsb_index_append_device(vsb_index *ix, const void *d_vectors, const int64_t *d_rowids, int64_t nrows) {
     if (check_index(ix)) return VSB_EINVAL;
     if (nrows < 0 || ix->n + nrows > ix->cap) return fail(VSB_ERANGE, "index capacity exceeded");
+    if (ix->streamed) return fail(VSB_EINVAL, "a streamed index takes host rows (vsb_index_append_dense / _quant_chunk)");
     CU(cudaSetDevice(ix->device));
     const size_t rowbytes = (size_t)ix->dim * ix->esize;
     if ((size_t)ix->pitch != rowbytes)
@@ -918,6 +1073,8 @@ int64_t vsb_index_stat(const vsb_index *ix, const char *name) {
     if (!strcmp(name, "tc_us")) return ix->st_tc_us;
     if (!strcmp(name, "batch_us")) return ix->st_batch_us;
     if (!strcmp(name, "tc_rows")) return ix->st_tc_rows;
+    if (!strcmp(name, "stream_bytes")) return ix->st_stream_bytes;
+    if (!strcmp(name, "stream_us")) return ix->st_stream_us;
     if (!strcmp(name, "fetch_bytes")) return (long long)kHeadBytes;
     if (!strcmp(name, "slots")) return kSlots;
     if (!strcmp(name, "filter_blocks")) return (ix->num_sms * kWarps + kFilterWarpsFast - 1) / kFilterWarpsFast;
@@ -953,6 +1110,13 @@ void vsb_index_free(vsb_index *ix) {
     }
     if (ix->d_dist_all) cudaFree(ix->d_dist_all);
     if (ix->d_vec) cudaFree(ix->d_vec);
+    if (ix->h_arena) cudaFreeHost(ix->h_arena);
+    for (int b = 0; b < 2; ++b) {
+        if (ix->d_win[b]) cudaFree(ix->d_win[b]);
+        if (ix->win_copied[b]) cudaEventDestroy(ix->win_copied[b]);
+        if (ix->win_scanned[b]) cudaEventDestroy(ix->win_scanned[b]);
+    }
+    if (ix->cstream) cudaStreamDestroy(ix->cstream);
     for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
     batch_free(ix);
     if (ix->fstream) cudaStreamDestroy(ix->fstream);

@@ -654,7 +654,7 @@ static int flush_chunk(sqlite3 *db, const char *tbl, const char *col, uint32_t n
 
 /* two passes over the column: global min/max, then [int64 LE rowid][dim x q8] rows packed into chunks of at most
  * max_memory bytes (vector_rebuild_quantization, :1147-1336) */
-static int rebuild_quantization(sqlite3_context *ctx, vcolumn *v, int qtype, uint64_t max_memory, uint32_t *total) {
+static int rebuild_quantization_host(sqlite3_context *ctx, vcolumn *v, int qtype, uint64_t max_memory, uint32_t *total) {
     sqlite3 *db = sqlite3_context_db_handle(ctx);
     const int dim = v->dim, vtype = v->vtype;
     const size_t qsize = 8 + (size_t)dim;
@@ -755,6 +755,141 @@ static void quant_fingerprint(sqlite3 *db, const vcolumn *v, sqlite3_int64 fp[4]
         for (int i = 0; i < 4; ++i) fp[i] = sqlite3_column_int64(st, i);
     sqlite3_finalize(st);
     sqlite3_free(sql);
+}
+
+/* The same build with the two arithmetic loops on the GPU (vsb_quantizer_*): SQLite still steps through the rows and writes the
+ * shadow table, the min / max reduction (:1224-1256) and the quantization into chunk bytes (:1281-1320) are kernels.  When the raw
+ * column fits in HBM it is retained during pass 1 and the table is stepped ONCE (the reference steps it twice).  Output bytes,
+ * chunk boundaries, rowid1 / rowid2 / counter columns and the stored scale / offset are identical (tests/golden/sql_surface.json). */
+static int rebuild_quantization_gpu(sqlite3_context *ctx, vcolumn *v, int qtype, uint64_t max_memory, uint32_t *total) {
+    sqlite3 *db = sqlite3_context_db_handle(ctx);
+    const int dim = v->dim, vtype = v->vtype;
+    const size_t qsize = 8 + (size_t)dim, need = (size_t)dim * (size_t)elem_size(vtype);
+    *total = 0;
+    char *sql = sqlite3_mprintf("SELECT COUNT(*) FROM %q;", v->tbl);
+    sqlite3_int64 count = sql ? query_int64(db, sql) : 0;
+    sqlite3_free(sql);
+    if (max_memory == 0) {
+        max_memory = (count == 0) ? DEFAULT_MAX_MEMORY : (uint64_t)count * qsize;
+        if (count <= 0) {
+            v->qtype = (qtype == VSB_QUANT_AUTO) ? VSB_QUANT_U8 : qtype;
+            v->scale = 1.0f;
+            v->offset = 0.0f;
+            return SQLITE_OK;
+        }
+    }
+    uint32_t max_vectors = (uint32_t)(max_memory / qsize);
+    if (max_vectors == 0) max_vectors = 1;
+    const int64_t block_rows = (int64_t)((4u << 20) / need) + 1;
+    vsb_quantizer *qz = 0;
+    uint8_t *block = 0, *chunk = 0;
+    int64_t *ids = 0;
+    size_t ids_cap = 0, nrows = 0;
+    sqlite3_stmt *st = 0;
+    int rc = SQLITE_OK;
+    if (vsb_quantizer_create(&qz, 0, vtype, dim, count) != VSB_OK) { fn_error(ctx, SQLITE_ERROR, "vector_quantize: %s", vsb_last_error()); return SQLITE_ERROR; }
+    block = (uint8_t *)malloc((size_t)block_rows * need);
+    chunk = (uint8_t *)malloc((size_t)max_vectors * qsize);
+    if (!block || !chunk) { rc = SQLITE_NOMEM; goto done; }
+    sql = sqlite3_mprintf("SELECT %q, %q FROM %q ORDER BY %q;", v->pk, v->col, v->tbl, v->pk);
+    rc = sql ? sqlite3_prepare_v2(db, sql, -1, &st, 0) : SQLITE_NOMEM;
+    sqlite3_free(sql);
+    if (rc != SQLITE_OK) goto done;
+    {   /* pass 1: min / max on the GPU, rowids remembered on the host */
+        int64_t nb = 0;
+        for (;;) {
+            rc = sqlite3_step(st);
+            if (rc == SQLITE_DONE) { rc = SQLITE_OK; break; }
+            if (rc != SQLITE_ROW) goto done;
+            if (sqlite3_column_type(st, 1) == SQLITE_NULL) continue;
+            const void *blob = sqlite3_column_blob(st, 1);
+            if (!blob) continue;
+            if ((size_t)sqlite3_column_bytes(st, 1) < need) {
+                fn_error(ctx, SQLITE_ERROR, "Invalid vector blob found at rowid %lld.", (long long)sqlite3_column_int64(st, 0));
+                rc = SQLITE_ERROR;
+                goto done;
+            }
+            if (nrows == ids_cap) {
+                size_t cap = ids_cap ? ids_cap * 2 : 65536;
+                int64_t *p = (int64_t *)realloc(ids, cap * sizeof(int64_t));
+                if (!p) { rc = SQLITE_NOMEM; goto done; }
+                ids = p; ids_cap = cap;
+            }
+            ids[nrows++] = sqlite3_column_int64(st, 0);
+            memcpy(block + (size_t)nb * need, blob, need);
+            if (++nb == block_rows) {
+                if (vsb_quantizer_minmax(qz, block, nb) != VSB_OK) { fn_error(ctx, SQLITE_ERROR, "vector_quantize: %s", vsb_last_error()); rc = SQLITE_ERROR; goto done; }
+                nb = 0;
+            }
+        }
+        if (nb > 0 && vsb_quantizer_minmax(qz, block, nb) != VSB_OK) { fn_error(ctx, SQLITE_ERROR, "vector_quantize: %s", vsb_last_error()); rc = SQLITE_ERROR; goto done; }
+    }
+    {
+        float lo, hi;
+        int negative = 0;
+        if (vsb_quantizer_minmax_result(qz, &lo, &hi, &negative) != VSB_OK) { fn_error(ctx, SQLITE_ERROR, "vector_quantize: %s", vsb_last_error()); rc = SQLITE_ERROR; goto done; }
+        if (qtype == VSB_QUANT_AUTO) qtype = negative ? VSB_QUANT_S8 : VSB_QUANT_U8;      /* :1258-1261 */
+        float abs_max = fmaxf(fabsf(lo), fabsf(hi));
+        v->scale = (qtype == VSB_QUANT_U8) ? (255.0f / (hi - lo)) : (127.0f / abs_max);  /* :1265-1268 */
+        v->offset = (qtype == VSB_QUANT_U8) ? lo : 0.0f;
+        v->qtype = qtype;
+    }
+    if (vsb_quantizer_retained_rows(qz) == (int64_t)nrows) {
+        /* pass 2 from HBM: the raw column stayed on the device */
+        for (size_t a = 0; a < nrows; a += max_vectors) {
+            size_t m = nrows - a < max_vectors ? nrows - a : max_vectors;
+            if (vsb_quantizer_encode(qz, 0, (int64_t)a, ids + a, (int64_t)m, v->offset, v->scale, qtype, chunk) != VSB_OK) {
+                fn_error(ctx, SQLITE_ERROR, "vector_quantize: %s", vsb_last_error()); rc = SQLITE_ERROR; goto done;
+            }
+            rc = flush_chunk(db, v->tbl, v->col, (uint32_t)m, chunk, m * qsize, ids[a], ids[a + m - 1]);
+            if (rc != SQLITE_OK) goto done;
+            *total += (uint32_t)m;
+        }
+    } else {
+        /* pass 2 streaming: step through the table again, one chunk of raw rows at a time */
+        uint8_t *raw = (uint8_t *)malloc((size_t)max_vectors * need);
+        if (!raw) { rc = SQLITE_NOMEM; goto done; }
+        rc = sqlite3_reset(st);
+        size_t a = 0, m = 0;
+        while (rc == SQLITE_OK) {
+            int s = sqlite3_step(st);
+            if (s != SQLITE_ROW && s != SQLITE_DONE) { rc = s; break; }
+            int have = 0;
+            if (s == SQLITE_ROW) {
+                if (sqlite3_column_type(st, 1) == SQLITE_NULL) continue;
+                const void *blob = sqlite3_column_blob(st, 1);
+                if (!blob) continue;
+                memcpy(raw + m * need, blob, need);
+                ++m;
+                have = 1;
+            }
+            if (m == max_vectors || (s == SQLITE_DONE && m > 0)) {
+                if (vsb_quantizer_encode(qz, raw, 0, ids + a, (int64_t)m, v->offset, v->scale, qtype, chunk) != VSB_OK) {
+                    fn_error(ctx, SQLITE_ERROR, "vector_quantize: %s", vsb_last_error()); rc = SQLITE_ERROR; break;
+                }
+                rc = flush_chunk(db, v->tbl, v->col, (uint32_t)m, chunk, m * qsize, ids[a], ids[a + m - 1]);
+                *total += (uint32_t)m;
+                a += m;
+                m = 0;
+            }
+            (void)have;
+            if (s == SQLITE_DONE) break;
+        }
+        free(raw);
+    }
+done:
+    sqlite3_finalize(st);
+    vsb_quantizer_free(qz);
+    free(block); free(chunk); free(ids);
+    return rc;
+}
+
+/* GPU when a device is present (the product path; the -m gpu tests assert its kernels ran), else the host loops: the build is not
+ * the scan hot path and a database must stay quantizable on a machine that only prepares it */
+static int rebuild_quantization(sqlite3_context *ctx, vcolumn *v, int qtype, uint64_t max_memory, uint32_t *total) {
+    const char *force = getenv("VSB_QUANTIZE_HOST");
+    if (vsb_device_count() > 0 && !(force && *force == '1')) return rebuild_quantization_gpu(ctx, v, qtype, max_memory, total);
+    return rebuild_quantization_host(ctx, v, qtype, max_memory, total);
 }
 
 /* stage every shadow-table chunk into HBM (the GPU counterpart of the loop at :1382-1394) */

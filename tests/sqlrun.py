@@ -28,13 +28,27 @@ for s in stmts:
         out.append({"rows": [[enc(v) for v in r] for r in rows]})
     except Exception as e:
         out.append({"error": str(e)})
+try:
+    import ctypes
+    h = ctypes.CDLL(lib + ".so")                       # the same mapping SQLite loaded: its launch counter
+    h.vsb_kernel_launches.restype = ctypes.c_int64
+    out.append({"kernel_launches": int(h.vsb_kernel_launches())})
+except (OSError, AttributeError):
+    out.append({"kernel_launches": None})              # the reference build has no such symbol
 print("\n@@JSON@@" + json.dumps(out), flush=True)
 '''
 
 
-def run_sql(lib_path: str, statements, timeout=600):
-    """lib_path without the .so suffix is fine (sqlite appends it).  Returns a list of {"rows": ...} | {"error": ...}."""
-    p = subprocess.run([sys.executable, "-c", CHILD, lib_path], input=json.dumps(statements), capture_output=True, text=True, timeout=timeout)
+def run_sql(lib_path: str, statements, timeout=600, env=None, want_launches=False):
+    """lib_path without the .so suffix is fine (sqlite appends it).  Returns a list of {"rows": ...} | {"error": ...}
+    (plus, with want_launches, the library's kernel launch count after the script as a last element)."""
+    r = _run_sql(lib_path, statements, timeout, env)
+    return r if want_launches else r[:-1]
+
+
+def _run_sql(lib_path, statements, timeout, env):
+    p = subprocess.run([sys.executable, "-c", CHILD, lib_path], input=json.dumps(statements), capture_output=True, text=True, timeout=timeout,
+                       env=None if env is None else dict(os.environ, **env))
     if p.returncode != 0:
         raise RuntimeError(f"sql child failed: {p.stderr[-2000:]}")
     for ln in p.stdout.splitlines():          # the reference printf()s diagnostics to stdout; find our marker

@@ -16,11 +16,42 @@ def _index(vtype, x, rowids=None):
     return ix
 
 
+@pytest.mark.parametrize("epi_chunk", [1, 0])
 @pytest.mark.parametrize("vtype", [po.I8, po.U8])
 @pytest.mark.parametrize("metric", METRICS)
-def test_batch_int_bit_exact(oracle, vtype, metric):
+def test_batch_int_bit_exact(oracle, vtype, metric, epi_chunk):
+    """epi_chunk = 1 (default): the epilogue tests 32-column chunks (max score vs the chunk's weakest bound) before any
+    per-column work; 0: every score against its own bound.  Same candidate log, same results."""
     import sqlite_vector_b200 as vs
     eng = vs.load_engine()
+    old_chunk = eng.set_option("epi_chunk", epi_chunk)
+    try:
+        _batch_int_bit_exact(oracle, eng, vtype, metric)
+    finally:
+        eng.set_option("epi_chunk", old_chunk)
+
+
+def test_batch_chunk_test_with_very_different_query_norms(oracle):
+    """queries whose bounds differ by orders of magnitude inside one 32-column chunk: the chunk test degrades to the
+    per-column test (it may never lose a hit)"""
+    import sqlite_vector_b200 as vs
+    rng = np.random.Generator(np.random.PCG64(99))
+    n, dim, nq, k = 40000, 128, 64, 20
+    x = rng.integers(-100, 101, (n, dim)).astype(np.int8)
+    q = rng.integers(-100, 101, (nq, dim)).astype(np.int8)
+    q[::3] //= 50                     # tiny norms next to full-range ones
+    q[1::7] = 0                       # zero vectors
+    ix = _index(po.I8, x)
+    rowids = np.arange(1, n + 1, dtype=np.int64)
+    for metric in METRICS:
+        res = ix.scan_topk(metric, q, k)
+        for b in range(nq):
+            want_ids, want_d = oracle.scan_dense(metric, po.I8, q[b], x, rowids, k)
+            assert np.array_equal(res[b][0], want_ids) and np.array_equal(res[b][1], want_d), (metric, b)
+    ix.close()
+
+
+def _batch_int_bit_exact(oracle, eng, vtype, metric):
     rng = np.random.Generator(np.random.PCG64(500 + 10 * vtype + metric))
     for (n, dim, nq, k) in [(20000, 128, 16, 20), (50000, 384, 100, 20), (30000, 200, 300, 33)]:
         x = po.convert(rng.standard_normal((n, dim), dtype=np.float32), vtype)

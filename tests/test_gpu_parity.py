@@ -369,3 +369,42 @@ def test_golden_special_value_distances(eng, vtype):
         fin = np.isfinite(want)
         assert np.all(np.abs(got[fin] - want[fin]) <= 1e-5 * np.maximum(np.abs(want[fin]), 1.0)), (vtype, m)
     ix.close()
+
+
+@pytest.mark.parametrize("vtype", TYPES)
+def test_quantizer_bytes_match_oracle(eng, oracle, vtype):
+    """vsb_quantizer_* (the GPU loops of vector_quantize, sqlite-vector.c:1224-1320) against the oracle's quantize /
+    build_quant_buffer (pinned to the reference): min / max / qtype decision and every output byte, both qtypes, retained and
+    streamed, including NaN / Inf / huge inputs and values that land exactly on .5"""
+    import sqlite_vector_b200 as vs
+    rng = np.random.Generator(np.random.PCG64(600 + vtype))
+    n, dim = 20_000, 37
+    xf = rng.standard_normal((n, dim), dtype=np.float32) * 3
+    xf[::97, 3] = np.round(xf[::97, 3] * 2) / 2                  # exact halves
+    x = po.convert(xf, vtype)
+    if vtype in (po.F32, po.F16, po.BF16):
+        sp, _ = _special_matrix(vtype, rng, 96, dim)
+        x[500:596] = sp
+        if vtype == po.F32:
+            x[700, 0] = np.float32(3e38); x[701, 1] = np.float32(-3e38); x[702, 2] = np.float32(1e10)
+    rowids = np.arange(n, dtype=np.int64) * 5 - 1000              # negative and positive rowids
+    scale0, offset0, qt0 = oracle.quant_params(vtype, x)
+    for retain in (n, 0):
+        qz = vs.api.Quantizer(vtype, dim, retain_rows=retain)
+        for a in range(0, n, 6000):
+            qz.minmax(x[a:a + 6000])
+        lo, hi, neg = qz.minmax_result()
+        assert qz.retained_rows == (n if retain else -1)
+        qt = po.Q_S8 if neg else po.Q_U8
+        assert qt == qt0
+        abs_max = max(abs(np.float32(lo)), abs(np.float32(hi)))
+        scale = np.float32(255.0) / (np.float32(hi) - np.float32(lo)) if qt == po.Q_U8 else np.float32(127.0) / np.float32(abs_max)
+        offset = np.float32(lo) if qt == po.Q_U8 else np.float32(0)
+        assert (np.float32(scale) == np.float32(scale0) or (np.isnan(scale) and np.isnan(scale0))) and (np.float32(offset) == np.float32(offset0) or (np.isnan(offset) and np.isnan(offset0))), (scale, scale0, offset, offset0)
+        for q, sc, off in ((po.Q_U8, np.float32(37.5), np.float32(-2.0)), (po.Q_S8, np.float32(31.0), np.float32(0.0)), (qt, np.float32(scale), np.float32(offset))):
+            if not np.isfinite(sc):
+                continue
+            want = oracle.build_quant_buffer(vtype, x, rowids, off, sc, q)
+            got = qz.encode(None if retain else x, rowids, float(off), float(sc), q)
+            assert np.array_equal(got, want), (vtype, retain, q, np.nonzero(got != want)[0][:10])
+        qz.close()

@@ -245,3 +245,20 @@ def test_k_sequence_and_transactions_through_sql():
     assert "Quantization table not found" in r[21].get("error", ""), r[21]
     assert "Invalid quantization type" in r[22].get("error", "")
     assert r[23] == {"rows": [[n]]} and r[24]["rows"] == r[19]["rows"]
+
+
+@pytest.mark.gpu
+def test_vector_quantize_on_the_gpu_matches_reference_golden():
+    """f2: with a device present vector_quantize runs its min / max and quantization loops as kernels (vsb_quantizer_*): the
+    shadow-table bytes, chunk boundaries and stored parameters must equal the reference's golden output exactly, the kernels
+    must actually have run, and the host loops (VSB_QUANTIZE_HOST=1) must give the same bytes."""
+    script = sql_cases.surface_script()
+    want = json.load(open(os.path.join(G, "sql_surface.json")))
+    gpu = run_sql(OURS, script, want_launches=True)
+    host = run_sql(OURS, script, env={"VSB_QUANTIZE_HOST": "1"}, want_launches=True)
+    assert gpu[-1]["kernel_launches"] > host[-1]["kernel_launches"], "vector_quantize did not launch its kernels"
+    for s, a, h, b in zip(script, gpu[:-1], host[:-1], want):
+        if _stmt(s) in SURFACE_DEVIATIONS:
+            continue
+        assert a == b, (_stmt(s), a, b)
+        assert h == b, (_stmt(s), h, b)

@@ -9,6 +9,7 @@
 #   tc_variants   experimental epilogue variants of tc_scan_kernel (timing + correctness)
 #   fp_scan       single-query scan timing for f32 / f16 / bf16 (10M x 384)        ncu_fp   ncu --set full of the f32 scan
 #   sqlbench      tools/sql_bench.py at n = 1M for both extensions
+#   stream        f3: single-query scan of a streamed (pinned host -> two device windows) 10M x 384 int8 index
 #   sanitizer     compute-sanitizer memcheck + racecheck over small scans / batches
 set -u
 TAG=$1; shift
@@ -27,12 +28,13 @@ for step in "$@"; do
     ncu_tc_int8) timeout 600 $NCU --set full --import-source on -k regex:tc_scan_kernel -s 3 -c 1 -f -o ${O}_tc_int8_full python tools/quick_batch.py --n 10000000 --dim 384 --vtype 5 --metric 1 --nq 1024 --iters 2 > /dev/null 2>&1; ls -la ${O}_tc_int8_full.ncu-rep ;;
     ncu_tc_bf16) timeout 600 $NCU --set full --import-source on -k regex:tc_scan_kernel -s 3 -c 1 -f -o ${O}_tc_bf16_full python tools/quick_batch.py --n 10000000 --dim 768 --vtype 3 --metric 4 --nq 1024 --iters 2 > /dev/null 2>&1; ls -la ${O}_tc_bf16_full.ncu-rep ;;
     tc_variants)
-      timeout 300 python tools/quick_batch.py --n 10000000 --dim 384 --vtype 5 --metric 1 --nq 1024 --iters 3 --sweep "${TC_SWEEP:-epi_max=0;epi_max=1}" 2>&1 | grep -v "iter 0" | tail -8 | tee ${O}_tc_variants.txt ;;
+      timeout 300 python tools/quick_batch.py --n 10000000 --dim 384 --vtype 5 --metric 1 --nq 1024 --iters 3 --sweep "${TC_SWEEP:-epi_chunk=0;epi_chunk=1}" 2>&1 | grep -v "iter 0" | tail -8 | tee ${O}_tc_variants.txt ;;
     fp_scan)
       for vt in 1 2 3; do timeout 300 python tools/quick_bench.py --n 10000000 --dim 384 --vtype $vt --metric 1 --iters 30 2>&1 | tail -1; done | tee ${O}_fp_scan.txt
       timeout 300 python tools/quick_bench.py --n 10000000 --dim 384 --vtype 2 --metric 4 --iters 30 2>&1 | tail -1 | tee -a ${O}_fp_scan.txt ;;
     ncu_fp)     timeout 600 $NCU --set full --import-source on -k regex:scan_kernel -s 8 -c 1 -f -o ${O}_scan_f32_full python tools/quick_bench.py --n 10000000 --dim 384 --vtype 1 --metric 1 --iters 10 > /dev/null 2>&1; ls -la ${O}_scan_f32_full.ncu-rep ;;
     sqlbench)   timeout 900 python tools/sql_bench.py --n 1000000 --dim 384 --queries 50 --which both 2>&1 | cut -c1-900 | tee ${O}_sql_bench.jsonl ;;
+    stream)     timeout 600 python tools/quick_stream.py 2>&1 | tail -1 | tee ${O}_stream.json ;;
     sanitizer)
       for tool in memcheck racecheck; do
         timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python tools/sanitizer_workload.py > ${O}_sanitizer_$tool.txt 2>&1
