@@ -16,6 +16,17 @@ TAG=$1; shift
 mkdir -p gpurun_out
 O=gpurun_out/$TAG
 NCU="ncu --clock-control none"
+# gpurun merges at most 64 MiB back: export what is read afterwards (raw metrics, details, per-line source counters) and drop the report
+export_rep() {
+  local rep=$1
+  [ -f "$rep.ncu-rep" ] || { echo "no report $rep"; return; }
+  ncu -i "$rep.ncu-rep" --page raw --csv > "${rep}_raw.csv" 2>/dev/null
+  ncu -i "$rep.ncu-rep" --page details > "${rep}_details.txt" 2>/dev/null
+  ncu -i "$rep.ncu-rep" --page source --csv > "${rep}_source.csv" 2>/dev/null
+  python tools/ncu_summary.py "${rep}_raw.csv" > "${rep}_summary.json" 2>/dev/null
+  rm -f "$rep.ncu-rep"
+  ls -la ${rep}_* | awk '{print $5, $9}'
+}
 for step in "$@"; do
   echo "=== [$TAG] $step  ($(date +%T))"
   case "$step" in
@@ -24,15 +35,15 @@ for step in "$@"; do
     bench)      timeout 900 python bench.py > ${O}_bench_n1.json 2> ${O}_bench_n1.err; tail -3 ${O}_bench_n1.err; python tools/bench_summary.py ${O}_bench_n1.json ;;
     bench_ref)  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > ${O}_bench_reference.json 2> ${O}_bench_reference.err; cut -c1-400 ${O}_bench_reference.json ;;
     launches)   timeout 600 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file ${O}_launches.csv python bench.py --steps 16 --warmup 3 --no-cpu-baseline > /dev/null 2>&1; tail -5 ${O}_launches.csv ;;
-    ncu_scan)   timeout 600 $NCU --set full --import-source on -k regex:scan_kernel -s 30 -c 1 -f -o ${O}_scan_full python bench.py --steps 40 --warmup 3 --no-cpu-baseline --no-batched > /dev/null 2>&1; ls -la ${O}_scan_full.ncu-rep ;;
-    ncu_tc_int8) timeout 600 $NCU --set full --import-source on -k regex:tc_scan_kernel -s 3 -c 1 -f -o ${O}_tc_int8_full python tools/quick_batch.py --n 10000000 --dim 384 --vtype 5 --metric 1 --nq 1024 --iters 2 > /dev/null 2>&1; ls -la ${O}_tc_int8_full.ncu-rep ;;
-    ncu_tc_bf16) timeout 600 $NCU --set full --import-source on -k regex:tc_scan_kernel -s 3 -c 1 -f -o ${O}_tc_bf16_full python tools/quick_batch.py --n 10000000 --dim 768 --vtype 3 --metric 4 --nq 1024 --iters 2 > /dev/null 2>&1; ls -la ${O}_tc_bf16_full.ncu-rep ;;
+    ncu_scan)   timeout 600 $NCU --set full --import-source on -k regex:scan_kernel -s 30 -c 1 -f -o ${O}_scan_full python bench.py --steps 40 --warmup 3 --no-cpu-baseline --no-batched > /dev/null 2>&1; export_rep ${O}_scan_full ;;
+    ncu_tc_int8) timeout 600 $NCU --set full --import-source on -k regex:tc_scan_kernel -s 5 -c 1 -f -o ${O}_tc_int8_full python tools/quick_batch.py --n 10000000 --dim 384 --vtype 5 --metric 1 --nq 1024 --iters 2 > /dev/null 2>&1; export_rep ${O}_tc_int8_full ;;
+    ncu_tc_bf16) timeout 600 $NCU --set full --import-source on -k regex:tc_scan_kernel -s 5 -c 1 -f -o ${O}_tc_bf16_full python tools/quick_batch.py --n 10000000 --dim 768 --vtype 3 --metric 4 --nq 1024 --iters 2 > /dev/null 2>&1; export_rep ${O}_tc_bf16_full ;;
     tc_variants)
       timeout 300 python tools/quick_batch.py --n 10000000 --dim 384 --vtype 5 --metric 1 --nq 1024 --iters 3 --sweep "${TC_SWEEP:-epi_chunk=0;epi_chunk=1}" 2>&1 | grep -v "iter 0" | tail -8 | tee ${O}_tc_variants.txt ;;
     fp_scan)
       for vt in 1 2 3; do timeout 300 python tools/quick_bench.py --n 10000000 --dim 384 --vtype $vt --metric 1 --iters 30 2>&1 | tail -1; done | tee ${O}_fp_scan.txt
       timeout 300 python tools/quick_bench.py --n 10000000 --dim 384 --vtype 2 --metric 4 --iters 30 2>&1 | tail -1 | tee -a ${O}_fp_scan.txt ;;
-    ncu_fp)     timeout 600 $NCU --set full --import-source on -k regex:scan_kernel -s 8 -c 1 -f -o ${O}_scan_f32_full python tools/quick_bench.py --n 10000000 --dim 384 --vtype 1 --metric 1 --iters 10 > /dev/null 2>&1; ls -la ${O}_scan_f32_full.ncu-rep ;;
+    ncu_fp)     timeout 600 $NCU --set full --import-source on -k regex:scan_kernel -s 8 -c 1 -f -o ${O}_scan_f32_full python tools/quick_bench.py --n 10000000 --dim 384 --vtype 1 --metric 1 --iters 10 > /dev/null 2>&1; export_rep ${O}_scan_f32_full ;;
     sqlbench)   timeout 900 python tools/sql_bench.py --n 1000000 --dim 384 --queries 50 --which both 2>&1 | cut -c1-900 | tee ${O}_sql_bench.jsonl ;;
     stream)     timeout 600 python tools/quick_stream.py 2>&1 | tail -1 | tee ${O}_stream.json ;;
     sanitizer)
