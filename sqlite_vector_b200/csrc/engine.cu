@@ -369,6 +369,7 @@ int ensure_workspace(vsb_index *ix, int k) {
 }
 
 unsigned exchange_next_seq(vsb_index *ix, int slot);
+int merge_blocks_strided(const uint8_t *blocks, int world, size_t stride, const int64_t *first_seq, int k, int64_t *out_rowids, double *out_dist);
 void exchange_free(vsb_index *ix);
 int exchange_fill_push(vsb_index *ix, PushParams *pp);
 
@@ -1314,27 +1315,7 @@ int vsb_result_block(vsb_index *ix, int slot_id, void **d_block, int64_t *bytes)
 int vsb_merge_result_blocks(const void *blocks, int world, int64_t block_stride, const int64_t *first_seq, int k, int64_t *out_rowids,
                             double *out_dist) {
     if (!blocks || world <= 0 || !first_seq || k <= 0 || !out_rowids || !out_dist) return fail(VSB_EINVAL, "bad merge arguments");
-    SlotState s{k, 0, out_dist, out_rowids};
-    slots_begin(s);
-    for (int r = 0; r < world; ++r) {   // shards are contiguous row ranges in rank order == scan order
-        const uint8_t *blk = (const uint8_t *)blocks + (size_t)r * (size_t)block_stride;
-        const int *hdr = (const int *)blk;
-        const int2 *table = (const int2 *)(blk + 64);
-        const uint2 *out = (const uint2 *)(blk + kResHdrBytes);
-        if (hdr[1]) return fail(VSB_ERANGE, "shard %d reported a candidate overflow", r);
-        if (hdr[0] > kFirstFetch) return fail(VSB_ERANGE, "shard %d has %d candidates (> %d in the exchanged block)", r, hdr[0], kFirstFetch);
-        const int nblocks = hdr[3];
-        for (int b = 0; b < nblocks; ++b) {
-            const int2 t = table[b];
-            for (int i = 0; i < t.y; ++i) {
-                const uint2 c = out[t.x + i];
-                float d;
-                memcpy(&d, &c.x, 4);
-                slots_offer(s, d, (int64_t)(first_seq[r] + (long long)c.y + 1));   // implicit rowids: global row + 1
-            }
-        }
-    }
-    return slots_finish(s);
+    return merge_blocks_strided((const uint8_t *)blocks, world, (size_t)block_stride, first_seq, k, out_rowids, out_dist);
 }
 
 int vsb_merge_result_groups(const void *blocks, int world, int64_t rank_stride, int64_t block_stride, int nq, const int64_t *first_seq,
