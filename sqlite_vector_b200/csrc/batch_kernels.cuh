@@ -144,48 +144,50 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *v) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Tile order.  Streaming mode (BSTAT=false): tile t = corpus-tile * NG + query-group, both operands streamed through
-// the stage ring.  B-stationary mode (BSTAT=true, small K): the whole query group [N x K] is parked in shared memory and
-// the CTA sweeps its corpus tiles for that group, then moves to the next group — 3x less L2->SM traffic at dim 384 int8.
-struct TileIter {
-    long long mt0, ntm;   // first corpus tile, number of corpus tiles of the level
-    int NG, grid, bid, bstat;
-    long long per_cta;    // corpus tiles owned by this CTA (bstat)
-    long long count;      // tiles this CTA processes
-    __device__ __forceinline__ void init(const TcParams &p, int bstat_) {
+// one lane of the calling (converged) warp; the same lane every time, so that the thread that issues the tcgen05.mma's also
+// issues their tcgen05.commit's.  Keeping the producer / MMA warps in warp-uniform control flow and electing only around the
+// asynchronous instructions lets the compiler hold descriptors, coordinates and barrier addresses in uniform registers: inside
+// an `if (lane == 0)` region it has to assume divergence and wraps every UTMALDG / UTCIMMA in an ELECT + R2UR.BROADCAST loop,
+// which made the single issuing thread — not the tensor pipe — the pace setter of short (K = 384 B) tiles (profiles/r02c).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// Tile order: tile t = corpus-tile * NG + query-group, t = blockIdx.x, + gridDim.x, ...  (both operands streamed through the
+// stage ring; the 4 query groups of one corpus tile run on different CTAs at about the same time, so the corpus tile is read
+// from HBM once and from L2 three times).  Walked incrementally: no division per tile.
+struct TileWalk {
+    long long mt0;        // first corpus tile of the level
+    uint32_t count;       // tiles this CTA processes
+    uint32_t q, r;        // current tile: corpus tile mt0 + q, query group r
+    uint32_t gq, gr, NG;  // gridDim.x = gq * NG + gr
+    __device__ __forceinline__ void init(const TcParams &p) {
         mt0 = p.r0 / kTcM;
-        ntm = (p.r1 + kTcM - 1) / kTcM - mt0;
-        NG = p.NG; grid = gridDim.x; bid = blockIdx.x; bstat = bstat_;
-        if (bstat) {
-            per_cta = (ntm > bid) ? (ntm - bid + grid - 1) / grid : 0;
-            count = per_cta * NG;
-        } else {
-            const long long total = ntm * NG;
-            per_cta = 0;
-            count = (total > bid) ? (total - bid + grid - 1) / grid : 0;
-        }
+        const long long ntm = (p.r1 + kTcM - 1) / kTcM - mt0;
+        const long long total = ntm * p.NG;
+        NG = (uint32_t)p.NG;
+        count = (total > (long long)blockIdx.x) ? (uint32_t)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+        q = blockIdx.x / NG; r = blockIdx.x % NG;
+        gq = gridDim.x / NG; gr = gridDim.x % NG;
     }
-    __device__ __forceinline__ void at(long long tl, long long &mt, int &ng) const {
-        if (bstat) {
-            ng = (int)(tl / per_cta);
-            mt = mt0 + bid + (tl % per_cta) * grid;
-        } else {
-            const long long t = bid + tl * grid;
-            mt = mt0 + t / NG;
-            ng = (int)(t % NG);
-        }
+    __device__ __forceinline__ long long mt() const { return mt0 + q; }
+    __device__ __forceinline__ int ng() const { return (int)r; }
+    __device__ __forceinline__ void next() {
+        q += gq; r += gr;
+        if (r >= NG) { r -= NG; ++q; }
     }
 };
 
 // CH: accumulator columns per epilogue step (64 = two 32-column TMEM loads in flight per buffer, 32 = one)
-// TEST: 0 = every score is compared with its query's bound (two dependent ALU ops per score: at K = 384 bytes the epilogue,
-//           not the MMA, set the tile time: tensor pipe 49 %, profiles/r01e_ncu_summary.json);
+// TEST: 0 = every score is compared with its query's bound (two dependent ALU ops per score);
 //       2 = chunk test (integer kinds, CH = 32; the default): the hit condition is monotone in the score, so a 32-column chunk
 //           can only contain a hit if  max_j s_ij  passes against the chunk's WEAKEST bound  min_j qc_j  (precomputed per chunk
 //           in shared memory).  The maximum costs 16 three-input VIMNMX per 32 scores instead of 64 dependent IADD3/ISETP, no
 //           per-column constants are loaded, and only chunks that pass (a few in 10^4 for queries of similar norm) run the
 //           per-column test that builds the exact hit masks.  The log is the same set of (row, query) pairs either way.
-template <int KIND, int MC, bool BSTAT, int EPI, int CH, int TEST = 0>
+template <int KIND, int MC, int EPI, int CH, int TEST = 0>
 __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, const TcParams prm) {
     constexpr int NACC = 2;                                                    // accumulator buffers in TMEM (2 x N <= 512 columns)
@@ -193,17 +195,14 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
     extern __shared__ __align__(1024) uint8_t tsm[];
     const int N = prm.N, NS = prm.nstages;
     const uint32_t a_bytes = kTcM * kTcKBytes, b_bytes = (uint32_t)N * kTcKBytes;
-    const uint32_t stage_bytes = BSTAT ? a_bytes : a_bytes + b_bytes;
-    uint8_t *stages = tsm;                                                     // [NS][A (| B)], 1024-aligned
-    uint8_t *bsm = tsm + (size_t)NS * stage_bytes;                             // BSTAT: [KB][N x 128 B]
-    uint8_t *tail = bsm + (BSTAT ? (size_t)prm.KB * b_bytes : 0);
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    uint8_t *stages = tsm;                                                     // [NS][A | B], 1024-aligned
+    uint8_t *tail = tsm + (size_t)NS * stage_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(tail);
     uint64_t *empty = full + kTcMaxStages;
     uint64_t *tfull = empty + kTcMaxStages;                                    // [NACC] accumulator ready
     uint64_t *tempty = tfull + NACC;                                           // [NACC] accumulator drained
-    uint64_t *bfull = tempty + NACC;                                           // BSTAT: query group landed / no longer read
-    uint64_t *bempty = bfull + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bempty + 1);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + NACC + 2);
     uint32_t *qc_s = tmem_slot + 4;                                            // [NG*N]
     uint32_t *qcm_s = qc_s + prm.NG * prm.N;                                   // [NG*N/32] weakest bound of each 32-column chunk (TEST = 2)
 
@@ -213,8 +212,6 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTcMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * EPI); }
-        mbar_init(bfull, 1);
-        mbar_init(bempty, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
@@ -239,83 +236,72 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
     }
     const uint32_t tmem_base = *tmem_slot;
 
-    TileIter ti;
-    ti.init(prm, BSTAT ? 1 : 0);
+    TileWalk tw;
+    tw.init(prm);
+    const int KB = prm.KB;
 
-    if (warp == 0) {
-        if (lane == 0) {                                                       // ===== TMA producer
-            int it = 0;
-            for (long long tl = 0; tl < ti.count; ++tl) {
-                long long mt; int ng;
-                ti.at(tl, mt, ng);
-                if constexpr (BSTAT) {
-                    if (tl % ti.per_cta == 0) {                                // new query group: park it in shared memory
-                        const int g = (int)(tl / ti.per_cta);
-                        mbar_wait(bempty, (uint32_t)((g & 1) ^ 1));
-                        mbar_expect_tx(bfull, (uint32_t)prm.KB * b_bytes);
-                        for (int kb = 0; kb < prm.KB; ++kb) tma_load_2d(bsm + (size_t)kb * b_bytes, &tmB, kb * kTcKBytes, ng * N, bfull);
-                    }
-                }
-                for (int kb = 0; kb < prm.KB; ++kb, ++it) {
-                    const int s = it % NS;
-                    mbar_wait(&empty[s], (uint32_t)(((it / NS) & 1) ^ 1));
+    if (warp == 0) {                                                           // ===== TMA producer: the whole warp walks, one lane issues
+        int s = 0;
+        uint32_t ph = 1;                                                       // parity to wait for on empty[s]: the first pass is free
+        for (uint32_t tl = 0; tl < tw.count; ++tl, tw.next()) {
+            const int row0 = (int)(tw.mt() * kTcM), col0 = tw.ng() * N;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&empty[s], ph);
+                if (elect_one()) {
                     mbar_expect_tx(&full[s], stage_bytes);
                     uint8_t *st = stages + (size_t)s * stage_bytes;
-                    tma_load_2d(st, &tmA, kb * kTcKBytes, (int)(mt * kTcM), &full[s]);
-                    if constexpr (!BSTAT) tma_load_2d(st + a_bytes, &tmB, kb * kTcKBytes, ng * N, &full[s]);
+                    tma_load_2d(st, &tmA, kb * kTcKBytes, row0, &full[s]);
+                    tma_load_2d(st + a_bytes, &tmB, kb * kTcKBytes, col0, &full[s]);
                 }
+                __syncwarp();
+                if (++s == NS) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {                                                       // ===== MMA issuer (one thread)
-            const uint32_t idesc = umma_idesc(KIND, N);
-            int it = 0;
-            for (long long tl = 0; tl < ti.count; ++tl) {
-                const int as = (int)(tl % NACC);
-                if constexpr (BSTAT) {
-                    if (tl % ti.per_cta == 0) mbar_wait(bfull, (uint32_t)((tl / ti.per_cta) & 1));
-                }
-                mbar_wait(&tempty[as], (uint32_t)(((tl / NACC) & 1) ^ 1));
+    } else if (warp == 1) {                                                    // ===== MMA issuer: the whole warp walks, one lane issues
+        const uint32_t idesc = umma_idesc(KIND, N);
+        int s = 0;
+        uint32_t ph = 0;                                                       // parity to wait for on full[s]
+        uint32_t as = 0, aph = 1;                                              // accumulator buffer, parity to wait for on tempty[as]
+        for (uint32_t tl = 0; tl < tw.count; ++tl) {
+            mbar_wait(&tempty[as], aph);
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + as * (uint32_t)N;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&full[s], ph);
                 tc_fence_after();
-                for (int kb = 0; kb < prm.KB; ++kb, ++it) {
-                    const int s = it % NS;
-                    mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint8_t *st = stages + (size_t)s * stage_bytes;
-                    const uint64_t ad = umma_desc_sw128(st);
-                    const uint64_t bd = umma_desc_sw128(BSTAT ? bsm + (size_t)kb * b_bytes : st + a_bytes);
+                    const uint64_t ad = umma_desc_sw128(st), bd = umma_desc_sw128(st + a_bytes);
 #pragma unroll
-                    for (int k4 = 0; k4 < kTcKBytes / 32; ++k4)                // UMMA_K = 32 bytes: advance start address by 2 (x16 B)
-                        tc_mma<INT8>(tmem_base + (uint32_t)(as * N), ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idesc, (uint32_t)((kb | k4) != 0));
+                    for (int k4 = 0; k4 < kTcKBytes / 32; ++k4)                // UMMA_K = 32 bytes: advance the start address by 2 (x16 B)
+                        tc_mma<INT8>(dcol, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idesc, (uint32_t)((kb | k4) != 0));
                     tc_commit(&empty[s]);                                      // frees the smem stage when these MMAs retire
+                    if (kb == KB - 1) tc_commit(&tfull[as]);                   // accumulator complete
                 }
-                tc_commit(&tfull[as]);                                         // accumulator complete
-                if constexpr (BSTAT) {
-                    if ((tl + 1) % ti.per_cta == 0) tc_commit(bempty);         // last tile of the group: B may be overwritten
-                }
+                __syncwarp();
+                if (++s == NS) { s = 0; ph ^= 1u; }
             }
+            if (++as == NACC) { as = 0; aph ^= 1u; }
         }
     } else if (warp >= 4) {                                                    // ===== epilogue: TMEM -> registers -> threshold test
         const int quad = warp & 3;                                             // TMEM lane quadrant this warp may read
         const int c_lo = ((warp - 4) >> 2) * (N / EPI), c_hi = c_lo + N / EPI;  // accumulator columns of this warp
-        // this thread's row norm of tile tl (raw bits; 0 for rows outside the level).  The load for tile tl+1 is issued while
-        // tile tl is tested: a global load per tile on the critical path was 7% of the epilogue's stall samples.
-        auto load_norm = [&](long long tl_) -> uint32_t {
-            if (tl_ >= ti.count) return 0u;
-            long long mt_; int ng_;
-            ti.at(tl_, mt_, ng_);
+        // this thread's row norm of the NEXT tile is loaded while the current one is tested (a global load per tile on the
+        // critical path was 7% of the epilogue's stall samples)
+        auto load_norm = [&](long long mt_) -> uint32_t {
             const long long row_ = mt_ * kTcM + quad * 32 + lane;
             return (row_ >= prm.r0 && row_ < prm.r1) ? reinterpret_cast<const uint32_t *>(prm.norms)[row_] : 0u;
         };
-        uint32_t nbits_next = load_norm(0);
-        for (long long tl = 0; tl < ti.count; ++tl) {
-            long long mt; int ng;
-            ti.at(tl, mt, ng);
-            const int as = (int)(tl % NACC);
+        uint32_t nbits_next = tw.count ? load_norm(tw.mt()) : 0u;
+        uint32_t as = 0, aph = 0;
+        for (uint32_t tl = 0; tl < tw.count; ++tl) {
+            const long long mt = tw.mt();
+            const int ng = tw.ng();
+            tw.next();
             const long long row = mt * kTcM + quad * 32 + lane;
             const bool rowvalid = row >= prm.r0 && row < prm.r1;
             const uint32_t nbits = nbits_next;
-            nbits_next = load_norm(tl + 1);
+            nbits_next = (tl + 1 < tw.count) ? load_norm(tw.mt()) : 0u;
             float rowf = 0.0f;
             int rowi = 0;
             if (rowvalid) {
@@ -328,7 +314,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
                     rowf = (MC == MC_L2) ? -nn * (1.0f - prm.eps) : __fsqrt_rn(nn);
                 }
             }
-            mbar_wait(&tfull[as], (uint32_t)((tl / NACC) & 1));
+            mbar_wait(&tfull[as], aph);
             tc_fence_after();
             // 64 accumulator columns per step, software pipelined: the TMEM loads of step i+1 are in flight while step i
             // is tested (TMEM reads are 64 B/clk/SM: 128x256 fp32 accumulators take >= 2048 clk to drain, which bounds
@@ -435,6 +421,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
+            if (++as == NACC) { as = 0; aph ^= 1u; }
         }
     }
     tc_fence_before();
@@ -645,6 +632,7 @@ __device__ __forceinline__ void warp_offer32(float *sd, unsigned *sr, int kcap, 
             const int cand = (key == mx) ? bi : 0x7FFFFFFF;
             mi = __reduce_min_sync(0xFFFFFFFFu, cand);
             cur = funkey(mx);
+            __syncwarp();                      // every lane has read the slots before lane 0 writes the next accepted offer (racecheck: WAR)
             on_accept(dv, rv);
         }
     }

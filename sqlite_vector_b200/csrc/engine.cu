@@ -40,7 +40,6 @@ int g_opt_no_batch = 0;        // 1: never take the tensor-core batch path
 int g_opt_batch_debug = 0;     // 1: print per-stage timings of the batch path to stderr (serialises the stages)
 int g_opt_batch_m0 = 128;      // batch path: rows refined exhaustively before the first tensor-core level
 int g_opt_batch_growth = 8;    // batch path: each tensor-core level covers rows [m, growth*m) (capped by k, see batch_growth)
-int g_opt_bstat = 0;           // 1: park the query group in shared memory when it fits (measured: no gain, off by default)
 int g_opt_fuse_mb = 0;         // > 0: vsb_scan_submit_group fuses a group into ONE scan launch when one query's scan reads less than this
                                // many MB (measured per query on one GPU: 84.0 -> 76.9 us at 0.48 GB; 2 GPUs: 285 -> 271 us at 1.92 GB).
                                // Off by default: a persistent 8-query launch leaves the NCCL all-gather of the previous group no SM until
@@ -845,7 +844,6 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "ring_bytes")) p = &g_opt_ring_bytes;
     else if (!strcmp(name, "time_kernels")) p = &g_opt_time_kernels;
     else if (!strcmp(name, "no_batch")) p = &g_opt_no_batch;
-    else if (!strcmp(name, "bstat")) p = &g_opt_bstat;
     else if (!strcmp(name, "epi2")) p = &g_opt_epi2;
     else if (!strcmp(name, "epi_chunk")) p = &g_opt_epi_chunk;
     else if (!strcmp(name, "balance")) p = &g_opt_balance;

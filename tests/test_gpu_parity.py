@@ -282,11 +282,11 @@ def _special_matrix(vtype, rng, n=96, dim=40):
     x[5, 1] = PINF
     x[6, 7] = NINF
     x[9, :] = 0
-    x[11, 4] = PINF; x[11, 30] = NINF            # mixed-sign infinities in one row (round-1 deviation 6)
-    x[12, 30] = PINF; x[12, 4] = NINF
+    x[11, 4] = PINF; x[11, dim - 10] = NINF      # mixed-sign infinities in one row (round-1 deviation 6)
+    x[12, dim - 10] = PINF; x[12, 4] = NINF
     x[13, 0] = NAN; x[13, 5] = PINF
     x[14, 3] = PINF; x[14, 9] = NAN; x[14, 20] = NINF
-    x[15, 39] = NINF                              # last element (tail loop of the reference)
+    x[15, dim - 1] = NINF                         # last element (tail loop of the reference)
     x[16, 8] = PINF; x[16, 9] = PINF
     return x, (NAN, PINF, NINF)
 
@@ -300,7 +300,7 @@ def test_special_values_all_fp_types(eng, oracle, vtype):
     x, (NAN, PINF, NINF) = _special_matrix(vtype, rng)
     dim = x.shape[1]
     queries = [x[0].copy(), x[5].copy(), x[11].copy(), x[9].copy()]
-    qz = x[1].copy(); qz[4] = 0; qz[30] = 0      # zeros where rows 11/12 hold infinities: Inf * 0
+    qz = x[1].copy(); qz[4] = 0; qz[dim - 10] = 0  # zeros where rows 11/12 hold infinities: Inf * 0
     queries.append(qz)
     qn = x[2].copy(); qn[8] = NAN; qn[3] = NINF
     queries.append(qn)

@@ -5,7 +5,7 @@ import sys
 d = json.load(open(sys.argv[1]))
 print({k: d.get(k) for k in ("value", "ms_per_step", "n_gpus", "gpu_launches")})
 print("e2e", d.get("e2e"))
-print("roofline", {k: d["roofline"].get(k) for k in ("achieved", "peak", "frac", "avg_launch_ms", "traffic")} if d.get("roofline") else None)
+print("roofline", {k: d["roofline"].get(k) for k in ("achieved", "peak", "frac", "avg_launch_ms", "traffic", "kernel_alone_ms", "kernel_alone_gbs", "tc_kernel_ms_per_batch", "hbm")} if d.get("roofline") else None)
 print("clocks", d.get("clocks"))
 for k, v in (d.get("batched") or {}).items():
     if isinstance(v, dict):

@@ -37,7 +37,7 @@ def read(path):
     for vals in rows[2:]:
         d = {"Kernel Name": [vals[hdr.index("Kernel Name")], ""]}
         for h, u, v in zip(hdr, units, vals):
-            if h in KEYS or "utcimma" in h or "utchmma" in h:
+            if h in KEYS:
                 d[h] = [v, u]
         res.append(d)
     return res[0] if len(res) == 1 else res
