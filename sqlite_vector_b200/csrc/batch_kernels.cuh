@@ -406,21 +406,29 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
                     }
                 }
             };
+            // the accumulator buffer is handed back to the MMA warp as soon as this warp's LAST TMEM load has landed in
+            // registers — before that chunk is tested: the MMA of tile t+2 waits for exactly this arrival (profiles/r02d: after the
+            // issue loops were fixed, the MMA <-> epilogue hand-over of the two buffers set the tile period, not either pipe)
+            auto release = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+            };
             uint32_t va[CH], vb[CH];
             issue(c_lo, va);
             for (int cb = c_lo; cb < c_hi; cb += 2 * CH) {
                 tmem_wait_ld();
-                if (cb + CH < c_hi) issue(cb + CH, vb);
+                const bool more1 = cb + CH < c_hi;
+                if (more1) issue(cb + CH, vb);
+                else release();
                 process(cb, va);
-                if (cb + CH < c_hi) {
+                if (more1) {
                     tmem_wait_ld();
                     if (cb + 2 * CH < c_hi) issue(cb + 2 * CH, va);
+                    else release();
                     process(cb + CH, vb);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
             if (++as == NACC) { as = 0; aph ^= 1u; }
         }
     }

@@ -4,6 +4,7 @@
 # Every step writes under gpurun_out/TAG_* (merged back by gpurun) and prints a short summary.  Steps:
 #   tests         pytest -m gpu (whole suite)            tests:<expr>   pytest -m gpu -k <expr>
 #   bench         bench.py (N=1, defaults)               bench_ref      bench.py --impl reference        bench_c4   bench.py --config c4 (N=1)
+#   bench_n:<N>[:tag[:args]]   torchrun bench.py --gpus N (needs gpurun --gpus N)
 #   launches      ncu launch list of a short bench run   ncu_scan       ncu --set full of scan_kernel (int8 10M x 384)
 #   ncu_tc_int8 / ncu_tc_bf16   ncu --set full of tc_scan_kernel (batch 1024)
 #   tc_variants   experimental epilogue variants of tc_scan_kernel (timing + correctness)
@@ -35,6 +36,11 @@ for step in "$@"; do
     tests:*)    timeout 1500 python -m pytest tests -x -q -m gpu -k "${step#tests:}" 2>&1 | tail -15 | tee ${O}_tests_k.txt ;;
     bench)      timeout 900 python bench.py > ${O}_bench_n1.json 2> ${O}_bench_n1.err; tail -3 ${O}_bench_n1.err; python tools/bench_summary.py ${O}_bench_n1.json ;;
     bench_c4)   timeout 900 python bench.py --config c4 --steps 5 --warmup 1 > ${O}_bench_c4_n1.json 2> ${O}_bench_c4_n1.err; tail -2 ${O}_bench_c4_n1.err; python tools/bench_summary.py ${O}_bench_c4_n1.json ;;
+    bench_n:*)  # bench_n:<N>[:tag[:extra bench.py args]]  -> torchrun, one rank per GPU
+      IFS=: read -r _ NG TAG2 EXTRA <<< "$step"
+      TAG2=${TAG2:-peer}
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((29700 + NG)) bench.py --gpus $NG $EXTRA > ${O}_bench_n${NG}_${TAG2}.json 2> ${O}_bench_n${NG}_${TAG2}.err
+      tail -3 ${O}_bench_n${NG}_${TAG2}.err | cut -c1-300; python tools/bench_summary.py ${O}_bench_n${NG}_${TAG2}.json ;;
     bench_ref)  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > ${O}_bench_reference.json 2> ${O}_bench_reference.err; cut -c1-400 ${O}_bench_reference.json ;;
     launches)   timeout 600 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file ${O}_launches.csv python bench.py --steps 16 --warmup 3 --no-cpu-baseline > /dev/null 2>&1; tail -5 ${O}_launches.csv ;;
     ncu_scan)   timeout 600 $NCU --set full --import-source on -k regex:scan_kernel -s 30 -c 1 -f -o ${O}_scan_full python bench.py --steps 40 --warmup 3 --no-cpu-baseline --no-batched > /dev/null 2>&1; export_rep ${O}_scan_full ;;
