@@ -274,7 +274,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c2", "c4"], help="c2: BASELINE configs[1] (the metric's config); c4: configs[3]")
-    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=0, help="corpus rows (--rows: torchrun's own parser rejects a bare --n as ambiguous)")
     ap.add_argument("--dim", type=int, default=0)
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--min-ms", type=float, default=50.0, help="repeat the K steps until the timed region lasts at least this long")
