@@ -526,11 +526,24 @@ def main():
     if world > 1 and not a.no_batched:
         try:
             B = 1024
-            shard.sharded_batch_topk(ix, api.L2, q_host[:B], k, bounds, device, as_arrays=True)   # warm-up: row norms, tensor maps
-            barrier()
-            nb, t0b = 5, time.perf_counter()
-            for _ in range(nb):
-                rb = shard.sharded_batch_topk(ix, api.L2, q_host[:B], k, bounds, device, as_arrays=True)
+            use_peer = a.exchange == "peer"
+            if use_peer:
+                # entry logs pushed over NVLink peer memory by the engine, device-side wait, GPU merge; two batches in flight
+                rb = exch.batch_finish(exch.batch_submit(api.L2, q_host[:B], k), as_arrays=True)   # warm-up: row norms, tensor maps
+                barrier()
+                nb, t0b, pending = 10, time.perf_counter(), None
+                for _ in range(nb):
+                    t = exch.batch_submit(api.L2, q_host[:B], k)
+                    if pending is not None:
+                        rb = exch.batch_finish(pending, as_arrays=True)
+                    pending = t
+                rb = exch.batch_finish(pending, as_arrays=True)
+            else:
+                shard.sharded_batch_topk(ix, api.L2, q_host[:B], k, bounds, device, as_arrays=True)   # warm-up
+                barrier()
+                nb, t0b = 5, time.perf_counter()
+                for _ in range(nb):
+                    rb = shard.sharded_batch_topk(ix, api.L2, q_host[:B], k, bounds, device, as_arrays=True)
             barrier()
             dtb = (time.perf_counter() - t0b) / nb
             t = torch.tensor([dtb], device=device)
@@ -542,7 +555,9 @@ def main():
                 batched_sharded = {"workload": f"vector_quantize_scan int8 dim={dim} n={n} k={k} batch={B} L2, {world} row shards",
                                    "queries_per_s": B / dtb, "ms_per_batch": dtb * 1e3, "batch": B,
                                    "end_to_end_tflops": 2.0 * dim * B * n / dtb / 1e12,
-                                   "path": "per shard: tcgen05 scoring + exact refine + slot replay with entry logs; NCCL all-gather of the logs; GPU merge replay",
+                                   "path": ("per shard: tcgen05 scoring + exact refine + slot replay with entry logs; the log blocks are pushed into every peer's log area over NVLink "
+                                            "(push_logs_kernel), device-side flag wait, GPU merge replay; two batches in flight, one host wait per batch" if use_peer else
+                                            "per shard: tcgen05 scoring + exact refine + slot replay with entry logs; NCCL all-gather of the logs; GPU merge replay"),
                                    "_result": rb}
         except Exception as ex:  # never lose the headline line
             batched_sharded = {"error": str(ex)}
@@ -839,10 +854,14 @@ def run_c4(torch, a, rank, local_rank, world):
     q = (torch.randn((B, dim), generator=g, device=device).abs_() * 48.0).round_().clamp_(0, 255).to(torch.uint8).cpu().numpy()
     log(f"[rank {rank}] c4 shard rows [{lo},{hi}) resident in {time.perf_counter() - t0:.1f}s")
 
+    exch = shard.PeerExchange(ix, eng, world, rank, bounds) if (world > 1 and a.exchange == "peer") else None
+
     def batch():
         if world == 1:
             r = ix.scan_topk(api.COSINE, q, k)
             return (np.stack([np.pad(x[0], (0, k - len(x[0]))) for x in r]), np.stack([np.pad(x[1], (0, k - len(x[1]))) for x in r]), np.array([len(x[0]) for x in r]))
+        if exch is not None:
+            return exch.batch_finish(exch.batch_submit(api.COSINE, q, k), as_arrays=True)
         return shard.sharded_batch_topk(ix, api.COSINE, q, k, bounds, device, as_arrays=True)
 
     def barrier():
@@ -863,8 +882,17 @@ def run_c4(torch, a, rank, local_rank, world):
     us0, rows0 = ix.stat("tc_us"), ix.stat("tc_rows")
     l0 = eng.kernel_launches()
     t0 = time.perf_counter()
-    for _ in range(K):
-        rb = batch()
+    if exch is not None:                      # two batches in flight
+        pending = None
+        for _ in range(K):
+            t = exch.batch_submit(api.COSINE, q, k)
+            if pending is not None:
+                rb = exch.batch_finish(pending, as_arrays=True)
+            pending = t
+        rb = exch.batch_finish(pending, as_arrays=True)
+    else:
+        for _ in range(K):
+            rb = batch()
     barrier()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -883,6 +911,11 @@ def run_c4(torch, a, rank, local_rank, world):
             same = all(np.array_equal(ix.scan_topk(api.COSINE, q[b], k)[0][0], rb[0][b]) and np.array_equal(ix.scan_topk(api.COSINE, q[b], k)[0][1], rb[1][b]) for b in (0, 100, 255))
         finally:
             eng.set_option("no_batch", 0)
+    elif exch is not None:                    # every rank takes part: the per-query exchange (k = 100: the generic filter path)
+        same = True
+        for b in (0, 100, 255):
+            one = exch.query(api.COSINE, q[b], k, on_device=False)
+            same = same and bool(np.array_equal(one[0], rb[0][b][:rb[2][b]]) and np.array_equal(one[1], rb[1][b][:rb[2][b]]))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -895,7 +928,7 @@ def run_c4(torch, a, rank, local_rank, world):
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic |N(0,1)|*48 rounded to uint8 (seed 1234); queries seed 4321",
            "config": {"workload": f"vector_quantize_scan cosine uint8 dim={dim} n={n} k={k} batch={B}", "shards": world, "rows_per_shard": hi - lo,
                       "l2_flush": "none needed: every batch streams the whole shard (%.1f GB)" % ((hi - lo) * dim / 1e9),
-                      "path": "per shard: tcgen05 (kind::i8) scoring + exact refine + slot replay" + ("" if world == 1 else " with entry logs; NCCL all-gather of the logs; GPU merge replay")},
+                      "path": "per shard: tcgen05 (kind::i8) scoring + exact refine + slot replay" + ("" if world == 1 else (" with entry logs; logs pushed over NVLink peer memory, device-side wait, GPU merge replay; two batches in flight" if exch is not None else " with entry logs; NCCL all-gather of the logs; GPU merge replay"))},
            "e2e": {"value": B * K / dt, "unit": "queries/s", "h2d_bytes_per_step": int(q.nbytes), "d2h_bytes_per_step": int(B * 128 * 8),
                    "note": "host queries in, host top-k out: the timed call IS the public C-ABI call (vsb_scan_topk / vsb_batch_shard_scan + vsb_batch_merge)"},
            "gpu_launches": int(launches),

@@ -184,6 +184,15 @@ VSB_API int vsb_exchange_submit(vsb_index *ix, int metric, const void *queries, 
 VSB_API int vsb_exchange_collect(vsb_index *ix, int first_slot, int nq, const int64_t *first_seq /* [world] */, int k,
                                  int64_t *out_rowids, double *out_dist, int *out_counts);
 
+/* batched queries over the same exchange (BASELINE config 4 between processes): every rank runs the tensor-core levels with entry
+ * logs over its shard, pushes its log block into every peer's log area over NVLink (push_logs_kernel), waits for the peers'
+ * flags on the device and replays all logs in shard order on its GPU — the result of one scan over the whole column on every
+ * rank, no collective library, ONE host wait per batch.  submit returns a ticket (0 / 1: two batches may be in flight) or a
+ * negative code (VSB_ERANGE: the batch path does not apply — use vsb_exchange_submit per query); collect returns VSB_ERANGE on
+ * EVERY rank when any shard exceeded a capacity.  out_seq holds GLOBAL scan-order rows (vsb_index_lookup_rowids / + 1). */
+VSB_API int vsb_exchange_batch_submit(vsb_index *ix, int metric, const void *queries, int nq, int k, const int64_t *first_seq);
+VSB_API int vsb_exchange_batch_collect(vsb_index *ix, int ticket, int nq, int k, int64_t *out_seq, double *out_dist, int *out_counts);
+
 /* ---- shard group: ONE column row-sharded over several GPUs inside one process (the SQLite extension, option gpus=N) --------
  * Replaces table_context.preloaded (src/sqlite-vector.c:135-136) by `ngpus` resident shards of contiguous row ranges in scan
  * order: shard s holds rows [capacity*s/ngpus, capacity*(s+1)/ngpus).  Rows are appended in scan order exactly like the
@@ -232,7 +241,7 @@ VSB_API int vsb_profile_read(vsb_index *ix, double *scan_ms, int *scan_launches,
 /* diagnostics: copies an internal device buffer of the most recent single-query scan to `out`; name in {"cta_time" (unsigned
  * cycles per scan CTA), "bounds" (int64 tile boundaries of the adaptive row partition)}.  Returns the bytes copied or < 0. */
 VSB_API int vsb_debug_read(vsb_index *ix, const char *name, void *out, int64_t bytes);
-/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","epi2","batch_debug","batch_m0","batch_growth","balance","fuse_mb","scan_streams","xwait_ms","epi_chunk"};
+/* tuning knobs for experiments: name in {"stage_bytes","direct","ring_bytes","time_kernels","no_batch","epi2","batch_debug","batch_m0","batch_growth","balance","fuse_mb","scan_streams","xwait_ms","epi_chunk","push_repeat" (experiment)};
  * values are non-negative; returns the previous value, or a negative VSB_E* code (unknown name, negative value) */
 VSB_API int vsb_set_option(const char *name, int value);
 

@@ -66,6 +66,8 @@ _SIGNATURES = {
     "vsb_exchange_attach": (_i, [_vp, _vp]),
     "vsb_exchange_submit": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _i]),
     "vsb_exchange_collect": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "vsb_exchange_batch_submit": (_i, [_vp, _i, _vp, _i, _i, _vp]),
+    "vsb_exchange_batch_collect": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "vsb_group_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i64]),
     "vsb_group_append_dense": (_i, [_vp, _vp, _vp, _i64]),
     "vsb_group_append_quant_chunk": (_i, [_vp, _vp, _i64]),
@@ -317,6 +319,21 @@ class Index:
         fs = np.ascontiguousarray(first_seq, dtype=np.int64)
         self.eng.check(self.eng.lib.vsb_exchange_collect(self.h, first_slot, nq, _ptr(fs), k, _ptr(ids), _ptr(dist), _ptr(counts)))
         return [(ids[j, :counts[j]], dist[j, :counts[j]]) for j in range(nq)]
+
+    def exchange_batch_submit(self, metric: int, queries: np.ndarray, k: int, first_seq: np.ndarray) -> int:
+        q2 = np.ascontiguousarray(queries).reshape(-1, queries.shape[-1])
+        fs = np.ascontiguousarray(first_seq, dtype=np.int64)
+        t = self.eng.lib.vsb_exchange_batch_submit(self.h, metric, _ptr(q2), q2.shape[0], k, _ptr(fs))
+        if t < 0:
+            self.eng.check(t)
+        return t
+
+    def exchange_batch_collect(self, ticket: int, nq: int, k: int):
+        seq = np.zeros((nq, k), dtype=np.int64)
+        dist = np.zeros((nq, k), dtype=np.float64)
+        counts = np.zeros(nq, dtype=np.int32)
+        self.eng.check(self.eng.lib.vsb_exchange_batch_collect(self.h, ticket, nq, k, _ptr(seq), _ptr(dist), _ptr(counts)))
+        return seq, dist, counts
 
     def collect(self, slot: int, k: int):
         ids = np.zeros(max(k, 1), dtype=np.int64)

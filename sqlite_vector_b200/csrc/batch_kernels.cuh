@@ -796,6 +796,10 @@ __global__ void merge_logs_kernel(const MergeParams mp) {
             if (lane == 0) atomicOr(mp.status, 2);
             return;
         }
+        if (hdr[3] != 0) {                      // the shard's levels exceeded a capacity (pushed blocks carry the flag, see push_logs_kernel)
+            if (lane == 0) atomicOr(mp.status, 1);
+            return;
+        }
         const int cnt = reinterpret_cast<const int *>(blk + acc_block_counts_off())[q];
         if (cnt > mp.acc_cap) {
             if (lane == 0) atomicOr(mp.status, 1);
@@ -808,6 +812,59 @@ __global__ void merge_logs_kernel(const MergeParams mp) {
             const uint2 e = (i < cnt) ? lg[i] : make_uint2(0x7F800000u, 0u);
             warp_offer32(sd, sr, mp.kcap, lane, __uint_as_float(e.x), base_row + e.y, mi, cur, [](float, unsigned) {});
         }
+    }
+}
+
+// ------------------------------------------------------------------ row-sharded batches: entry logs over NVLink peer memory
+// The counterpart of the head push in filter_kernel for the batched path: after the last level every shard stores the USED
+// part of its entry-log block (header, counts, `count` entries per query) into row `src` of every target's log area and raises
+// the target's flag when all of its blocks have fenced.  grid = (targets, slices); the header travels with the shard's overflow
+// flags (stats[2]) in hdr[3], so every rank reaches the same verdict without a host round trip.
+struct LogPushParams {
+    const uint8_t *block;        // local entry-log block (acc_block layout)
+    const unsigned *stats;       // [2] = overflow flags of this batch's levels
+    int nq, acc_cap;
+    int ntargets, src, world, buf;
+    unsigned bseq;
+    unsigned long long slot_stride;   // bytes between the rows of a target's log area
+    uint8_t *xlog[kMaxPeers];    // target t: base of its log area [2][world][slot_stride]
+    unsigned *lflags[kMaxPeers]; // target t: [2][world] arrival flags
+    unsigned *done;              // [targets] local block counters (zero before the launch, re-armed by the last block)
+};
+__global__ void push_logs_kernel(const LogPushParams lp) {
+    const int t = blockIdx.x, S = gridDim.y, j = blockIdx.y;
+    uint8_t *dst = lp.xlog[t] + ((size_t)lp.buf * lp.world + lp.src) * lp.slot_stride;
+    const size_t log_off = acc_block_log_off(lp.nq);
+    if (j == 0) {                                                   // header + counts
+        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(lp.block);
+        uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+        for (size_t i = threadIdx.x; i < log_off / 4; i += blockDim.x) d32[i] = (i == 3) ? lp.stats[2] : src32[i];
+    }
+    const int *counts = reinterpret_cast<const int *>(lp.block + acc_block_counts_off());
+    for (int q = j; q < lp.nq; q += S) {
+        const int cnt = min(max(counts[q], 0), lp.acc_cap);
+        const uint2 *s2 = reinterpret_cast<const uint2 *>(lp.block + log_off) + (size_t)q * lp.acc_cap;
+        uint2 *d2 = reinterpret_cast<uint2 *>(dst + log_off) + (size_t)q * lp.acc_cap;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) d2[i] = s2[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(&lp.done[t], 1u);
+        if (prev == (unsigned)S - 1u) {                              // every block of this target has fenced its stores
+            lp.done[t] = 0u;
+            st_release_sys(lp.lflags[t] + (size_t)lp.buf * lp.world + lp.src, lp.bseq);
+        }
+    }
+}
+// receiving side: wait until the `n` flags carry `expect`; bounded (status |= 4 on timeout)
+__global__ void log_wait_kernel(const unsigned *flags, int n, unsigned expect, long long timeout, int *status) {
+    const int t = threadIdx.x;
+    if (t >= n) return;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flags + t) != expect) {
+        if (clock64() - t0 > timeout) { atomicOr(status, 4); break; }
+        __nanosleep(200);
     }
 }
 

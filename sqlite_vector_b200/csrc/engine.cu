@@ -46,11 +46,12 @@ int g_opt_fuse_mb = 0;         // > 0: vsb_scan_submit_group fuses a group into 
                                // it ends (2 GPUs: the step-vs-scan gap grew from 3 to 14 us per query), not yet measured at 8 GPUs.
 int g_opt_balance = 1;         // 1: adaptive row partition of the single-query scan (per-CTA speeds feed the next partition)
 int g_opt_epi_chunk = 1;       // 1: integer tensor-core epilogue tests 32-column chunks (max score vs weakest bound) before any per-column work
-int g_opt_epi2 = 2;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 2 = 8 epilogue warps, two per TMEM lane quadrant
+int g_opt_epi2 = 4;            // epilogue shape of tc_scan_kernel (see launch_tc_mc): 4 = 16 epilogue warps where that variant exists (integer kinds, 256-query tiles), else 8; 2 = 8 warps; 0 = 4 warps
 int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA events (bench.py roofline leg)
 int g_opt_scan_streams = 2;    // 2: consecutive scan launches alternate between two streams, so the CTAs of launch i+1 take over each SM
                                // as soon as the CTA of launch i on it exits (one scan CTA fits per SM): no grid-wide drain between
                                // launches, per-SM speed differences turn into an earlier start of the next query.  1: one stream.
+int g_opt_push_repeat = 1;     // experiment: push every exchange target this many times (see exchange_fill_push)
 int g_opt_xwait_ms = 2000;     // exchange: how long the receiving side waits for a peer's head before it reports an error
 
 // cudaFuncSetAttribute costs ~1 us per call; the dynamic shared memory limit of a kernel only ever needs to grow
@@ -853,6 +854,7 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "batch_debug")) p = &g_opt_batch_debug;
     else if (!strcmp(name, "scan_streams")) p = &g_opt_scan_streams;
     else if (!strcmp(name, "xwait_ms")) p = &g_opt_xwait_ms;
+    else if (!strcmp(name, "push_repeat")) p = &g_opt_push_repeat;
     if (!p) return fail(VSB_EINVAL, "unknown option %s", name);
     if (value < 0) return fail(VSB_EINVAL, "option %s: values are non-negative", name);   // so that a negative return is always an error
     int old = *p;

@@ -183,6 +183,22 @@ class PeerExchange:
     def d2h_bytes_per_query(self) -> int:
         return self.world * self.stride
 
+    # ---- batched queries over the same exchange (implicit rowids: rowid = global row + 1)
+    def batch_submit(self, metric: int, queries: np.ndarray, k: int):
+        """tensor-core levels on this shard + push of the entry logs to every peer + device-side wait + GPU merge, all enqueued;
+        returns a ticket for batch_finish (two batches may be in flight).  Raises VsbError(rc = ERANGE) when the batch path does
+        not apply: use the per-query exchange then."""
+        q2 = np.ascontiguousarray(queries).reshape(-1, queries.shape[-1])
+        return self.ix.exchange_batch_submit(metric, q2, k, self.first_seq), q2.shape[0], k
+
+    def batch_finish(self, ticket, as_arrays: bool = False):
+        t, nq, k = ticket
+        seq, d, counts = self.ix.exchange_batch_collect(t, nq, k)
+        ids = seq + 1
+        if as_arrays:
+            return ids, d, counts
+        return [(ids[b, :counts[b]].copy(), d[b, :counts[b]].copy()) for b in range(nq)]
+
 
 def sharded_batch_topk(ix, metric: int, queries: np.ndarray, k: int, bounds, device, implicit_rowids: bool = True, as_arrays: bool = False):
     """Batched queries over a row-sharded column (BASELINE config 4).  Every rank runs the tensor-core batch path over

@@ -222,6 +222,35 @@ eng.set_option("fuse_mb", 0)
 r1 = exch.query(api.L1, q[3], 7, on_device=False)
 want_ids, want_d = orc.scan_dense(po.L1, po.I8, q[3], x, rowids, 7)
 assert np.array_equal(r1[0], want_ids) and np.array_equal(r1[1], want_d)
+# ---- batched queries: entry logs pushed over peer memory, device-side wait, GPU merge; two batches in flight
+qb = rng.integers(-6, 7, (70, dim)).astype(np.int8)
+for metric, kk in ((api.L2, 20), (api.COSINE, 100), (api.DOT, 7)):
+    t1 = exch.batch_submit(metric, qb[:40], kk)
+    t2 = exch.batch_submit(metric, qb[40:], kk)
+    res = exch.batch_finish(t1) + exch.batch_finish(t2)
+    for b in range(70):
+        want_ids, want_d = orc.scan_dense(metric, po.I8, qb[b], x, rowids, kk)
+        assert np.array_equal(res[b][0], want_ids) and np.array_equal(res[b][1], want_d), (rank, "batch", metric, b)
+# a shard-local capacity overflow (descending distances: every row enters the slots) must reach EVERY rank as ERANGE
+xo = np.zeros((n, 16), dtype=np.int8)
+xo[:, 0] = np.clip((n - 1 - np.arange(n)) // 1600, 0, 124).astype(np.int8)
+xo[:, 1] = ((n - 1 - np.arange(n)) % 1600 // 13).astype(np.int8)
+ixo = vs.Index(api.I8, 16, hi - lo, device=local, first_seq=lo)
+ixo.append_dense(xo[lo:hi]); ixo.finalize()
+exo = shard.PeerExchange(ixo, eng, world, rank, bounds, group=8)
+overflowed = 0
+try:
+    exo.batch_finish(exo.batch_submit(api.L2, np.zeros((16, 16), dtype=np.int8), 5))
+except vs.VsbError as ex:
+    assert ex.rc == api.ERANGE, ex
+    overflowed = 1
+flags = [None] * world
+dist.all_gather_object(flags, overflowed)
+assert flags == [1] * world, flags            # the verdict travels inside the pushed blocks: the same on every rank
+# the first exchange is unaffected
+r2 = exch.query(api.L2, q[5], 9, on_device=False)
+want_ids, want_d = orc.scan_dense(po.L2, po.I8, q[5], x, rowids, 9)
+assert np.array_equal(r2[0], want_ids) and np.array_equal(r2[1], want_d)
 dist.barrier()
 if rank == 0: print("PEER_EXCHANGE_OK", world, "ranks on", min(world, ndev), "GPU(s)")
 dist.destroy_process_group()
