@@ -51,6 +51,7 @@ int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA event
 int g_opt_scan_streams = 2;    // 2: consecutive scan launches alternate between two streams, so the CTAs of launch i+1 take over each SM
                                // as soon as the CTA of launch i on it exits (one scan CTA fits per SM): no grid-wide drain between
                                // launches, per-SM speed differences turn into an earlier start of the next query.  1: one stream.
+int g_opt_push_mode = 0;       // exchange: 0 = the filter's last block pushes the head (fused); 1 = a small kernel on the exchange stream pushes a finished group
 int g_opt_push_repeat = 1;     // experiment: push every exchange target this many times (see exchange_fill_push)
 int g_opt_xwait_ms = 2000;     // exchange: how long the receiving side waits for a peer's head before it reports an error
 
@@ -469,6 +470,7 @@ int launch_scan_group(vsb_index *ix, int metric, const uint8_t *const *d_queries
         if (push) {
             const int rc = exchange_fill_push(ix, &f.push);
             if (rc) return rc;
+            if (g_opt_push_mode == 1) f.push.ntargets = 0;      // the heads are pushed by push_heads_kernel (exchange_push); src / world still label the header
         }
         f.S = ix->ws_streams;
         f.k = k;
@@ -855,6 +857,7 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "scan_streams")) p = &g_opt_scan_streams;
     else if (!strcmp(name, "xwait_ms")) p = &g_opt_xwait_ms;
     else if (!strcmp(name, "push_repeat")) p = &g_opt_push_repeat;
+    else if (!strcmp(name, "push_mode")) p = &g_opt_push_mode;
     if (!p) return fail(VSB_EINVAL, "unknown option %s", name);
     if (value < 0) return fail(VSB_EINVAL, "option %s: values are non-negative", name);   // so that a negative return is always an error
     int old = *p;

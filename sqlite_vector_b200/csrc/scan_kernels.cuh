@@ -671,8 +671,10 @@ struct PushParams {
     int src;                      // this shard's index inside a slot's gather row
     int world;                    // shards per slot in the gather layout [slots][world][head_bytes]
     int head_bytes, res_hdr_bytes;// layout of a head: [hdr 64 B][table][survivors from res_hdr_bytes on]
+    int tailcap;                  // survivors beyond the head's headcap travel to a separate tail row of this many entries
     uint8_t *gather[kMaxPeers];   // target t: base of its gather buffer
     unsigned *flags[kMaxPeers];   // target t: [slots][world] arrival flags (the exchange sequence number of the slot)
+    uint2 *tails[kMaxPeers];      // target t: [slots][world][tailcap] tail rows (k > 32 on large shards: > headcap survivors)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
@@ -707,6 +709,50 @@ __global__ void exchange_wait_kernel(const WaitParams wp) {
         }
         __nanosleep(200);
     }
+}
+
+// the push itself: one block stores the used part of one finished head (header, block table, survivors; the survivors beyond
+// headcap from the slot's tail area) into row (xslot, src) of every target and raises the targets' flags.  All threads of the
+// block call it; the caller guarantees that the head is complete and visible (filter_kernel: last block; push_heads_kernel:
+// stream order after the filters).
+__device__ __forceinline__ void push_one_head(const PushParams &pp, const int *hdr, const uint2 *out, const uint2 *out_tail, int xslot, unsigned xseq,
+                                              int headcap) {
+    const int total = max(__ldcg(hdr), 0), nblocks = __ldcg(hdr + 3);
+    const int nhead = 8 + nblocks;                                         // uint2 words of header + block table
+    const int nsurv = min(total, headcap);
+    const int ntail = min(max(total - headcap, 0), pp.tailcap);
+    const uint2 *src_head = reinterpret_cast<const uint2 *>(hdr);
+    const size_t row = (size_t)xslot * pp.world + pp.src;
+    for (int t = 0; t < pp.ntargets; ++t) {
+        uint8_t *dst = pp.gather[t] + row * (size_t)pp.head_bytes;
+        uint2 *dh = reinterpret_cast<uint2 *>(dst);
+        uint2 *ds = reinterpret_cast<uint2 *>(dst + pp.res_hdr_bytes);
+        for (int i = (int)threadIdx.x; i < nhead; i += (int)blockDim.x) dh[i] = __ldcg(src_head + i);
+        for (int i = (int)threadIdx.x; i < nsurv; i += (int)blockDim.x) ds[i] = __ldcg(out + i);
+        if (ntail > 0) {
+            uint2 *dt = pp.tails[t] + row * (size_t)pp.tailcap;
+            for (int i = (int)threadIdx.x; i < ntail; i += (int)blockDim.x) dt[i] = __ldcg(out_tail + i);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pp.ntargets) st_release_sys(pp.flags[threadIdx.x] + row, xseq);
+}
+
+// option push_mode = 1: the heads of a finished group are pushed by their own small kernel on the exchange stream instead of by
+// the filter's last block (the filter stream then never waits for NVLink acknowledgements)
+struct PushGroupParams {
+    PushParams push;
+    int nq, headcap;
+    const int *hdr[kMaxGroup];
+    const uint2 *out[kMaxGroup];
+    const uint2 *out_tail[kMaxGroup];
+    int xslot[kMaxGroup];
+    unsigned xseq[kMaxGroup];
+};
+__global__ void push_heads_kernel(const PushGroupParams gp) {
+    const int j = blockIdx.x;
+    if (j < gp.nq) push_one_head(gp.push, gp.hdr[j], gp.out[j], gp.out_tail[j], gp.xslot[j], gp.xseq[j], gp.headcap);
 }
 
 struct FilterParams {
@@ -955,6 +1001,7 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
             fq.hdr[3] = (int)gridDim.x;
             fq.hdr[4] = (int)fq.xseq;
             fq.hdr[5] = fp.push.src;
+            fq.hdr[6] = fp.headcap;
             fq.ctrl[0] = 0; fq.ctrl[1] = 0; fq.ctrl[2] = 0;
             push_total = total;
         }
@@ -965,21 +1012,7 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
         if (is_last) {
             // the other blocks' survivors are visible: each fenced before its ctrl[2] increment, thread 0 fenced after
             // observing the last one; read them through L2 (ld.cg), store them to peer memory over NVLink
-            const PushParams &pp = fp.push;
-            const int nhead = 8 + (int)gridDim.x;                                  // uint2 words of header + block table
-            const int nsurv = min(max(push_total, 0), fp.headcap);
-            const uint2 *src_head = reinterpret_cast<const uint2 *>(fq.hdr);
-            for (int t = 0; t < pp.ntargets; ++t) {
-                uint8_t *dst = pp.gather[t] + ((size_t)fq.xslot * pp.world + pp.src) * (size_t)pp.head_bytes;
-                uint2 *dh = reinterpret_cast<uint2 *>(dst);
-                uint2 *ds = reinterpret_cast<uint2 *>(dst + pp.res_hdr_bytes);
-                for (int i = (int)threadIdx.x; i < nhead; i += (int)blockDim.x) dh[i] = __ldcg(src_head + i);
-                for (int i = (int)threadIdx.x; i < nsurv; i += (int)blockDim.x) ds[i] = __ldcg(fq.out + i);
-            }
-            __threadfence_system();
-            __syncthreads();
-            if ((int)threadIdx.x < pp.ntargets)
-                st_release_sys(pp.flags[threadIdx.x] + (size_t)fq.xslot * pp.world + pp.src, fq.xseq);
+            push_one_head(fp.push, fq.hdr, fq.out, fq.out_tail, fq.xslot, fq.xseq, fp.headcap);
         }
     }
 }

@@ -42,6 +42,15 @@ def _group(vtype, x, ngpus, rowids=None, chunk=7919):
 
 @pytest.mark.parametrize("ngpus", [2, 3, 8])
 def test_group_int8_bit_exact(oracle, ngpus):
+    import sqlite_vector_b200 as vs
+    old_pm = vs.load_engine().set_option("push_mode", 1 if ngpus == 3 else 0)     # one of the three also through the separate push kernel
+    try:
+        _group_int8_bit_exact(oracle, ngpus)
+    finally:
+        vs.load_engine().set_option("push_mode", old_pm)
+
+
+def _group_int8_bit_exact(oracle, ngpus):
     rng = np.random.Generator(np.random.PCG64(100 + ngpus))
     n, dim = 50_000, 64
     x = rng.integers(-5, 6, (n, dim)).astype(np.int8)        # narrow value range: ties at the k-th place
@@ -222,6 +231,18 @@ eng.set_option("fuse_mb", 0)
 r1 = exch.query(api.L1, q[3], 7, on_device=False)
 want_ids, want_d = orc.scan_dense(po.L1, po.I8, q[3], x, rowids, 7)
 assert np.array_equal(r1[0], want_ids) and np.array_equal(r1[1], want_d)
+# k = 256: more than 1024 survivors per shard -> the tails travel too; and the separate push kernel (push_mode = 1)
+for pm in (1, 0):
+    eng.set_option("push_mode", pm)
+    for kk in (256, 20):
+        for b in (0, 7):
+            rr = exch.query(api.L2, q[b], kk, on_device=False)
+            want_ids, want_d = orc.scan_dense(po.L2, po.I8, q[b], x, rowids, kk)
+            assert np.array_equal(rr[0], want_ids) and np.array_equal(rr[1], want_d), (rank, "push_mode", pm, kk, b)
+    t = exch.submit_strided(api.DOT, q[8:16], q.strides[0], 8, 20, False)
+    for j, rr in enumerate(exch.finish(t)):
+        want_ids, want_d = orc.scan_dense(po.DOT, po.I8, q[8 + j], x, rowids, 20)
+        assert np.array_equal(rr[0], want_ids) and np.array_equal(rr[1], want_d), (rank, "push_mode group", pm, j)
 # ---- batched queries: entry logs pushed over peer memory, device-side wait, GPU merge; two batches in flight
 qb = rng.integers(-6, 7, (70, dim)).astype(np.int8)
 for metric, kk in ((api.L2, 20), (api.COSINE, 100), (api.DOT, 7)):
