@@ -285,6 +285,7 @@ def main():
     ap.add_argument("--group", type=int, default=8, help="sharded runs: queries per exchange group")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="sharded single queries: NVLink peer-memory push (engine) or NCCL all-gather (round 1)")
     ap.add_argument("--engine-opt", action="append", default=[], help="name=value passed to vsb_set_option (experiments)")
+    ap.add_argument("--batch-depth", type=int, default=2, choices=[1, 2], help="sharded batches over the peer exchange: batches in flight")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -534,10 +535,14 @@ def main():
                 nb, t0b, pending = 10, time.perf_counter(), None
                 for _ in range(nb):
                     t = exch.batch_submit(api.L2, q_host[:B], k)
+                    if a.batch_depth == 1:
+                        rb = exch.batch_finish(t, as_arrays=True)
+                        continue
                     if pending is not None:
                         rb = exch.batch_finish(pending, as_arrays=True)
                     pending = t
-                rb = exch.batch_finish(pending, as_arrays=True)
+                if pending is not None:
+                    rb = exch.batch_finish(pending, as_arrays=True)
             else:
                 shard.sharded_batch_topk(ix, api.L2, q_host[:B], k, bounds, device, as_arrays=True)   # warm-up
                 barrier()
@@ -882,7 +887,7 @@ def run_c4(torch, a, rank, local_rank, world):
     us0, rows0 = ix.stat("tc_us"), ix.stat("tc_rows")
     l0 = eng.kernel_launches()
     t0 = time.perf_counter()
-    if exch is not None:                      # two batches in flight
+    if exch is not None and a.batch_depth == 2:   # two batches in flight
         pending = None
         for _ in range(K):
             t = exch.batch_submit(api.COSINE, q, k)

@@ -51,7 +51,7 @@ int g_opt_time_kernels = 0;    // 1: bracket every kernel launch with CUDA event
 int g_opt_scan_streams = 2;    // 2: consecutive scan launches alternate between two streams, so the CTAs of launch i+1 take over each SM
                                // as soon as the CTA of launch i on it exits (one scan CTA fits per SM): no grid-wide drain between
                                // launches, per-SM speed differences turn into an earlier start of the next query.  1: one stream.
-int g_opt_push_mode = 0;       // exchange: 0 = the filter's last block pushes the head (fused); 1 = a small kernel on the exchange stream pushes a finished group
+int g_opt_push_mode = 1;       // exchange: 1 (default) = a small kernel on the exchange stream pushes a finished group's heads; 0 = the filter's last block pushes its head itself (fused: costs ~2 us per query with 8 targets, profiles/r02j)
 int g_opt_push_repeat = 1;     // experiment: push every exchange target this many times (see exchange_fill_push)
 int g_opt_xwait_ms = 2000;     // exchange: how long the receiving side waits for a peer's head before it reports an error
 
