@@ -52,6 +52,19 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// wait with back-off: the epilogue warps of an MMA-bound tile (long K) spend most of their time here, and 8 - 16 warps polling
+// an mbarrier in shared memory compete with the tensor core's operand reads and with the producer / MMA warps' issue slots
+// (config 4, dim 1536: 16 polling epilogue warps cost 40 % of the batch time, profiles/r02k)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    while (!done) {
+        __nanosleep(128);
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -314,7 +327,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) tc_scan_kernel(const __gri
                     rowf = (MC == MC_L2) ? -nn * (1.0f - prm.eps) : __fsqrt_rn(nn);
                 }
             }
-            mbar_wait(&tfull[as], aph);
+            mbar_wait_backoff(&tfull[as], aph);
             tc_fence_after();
             // 64 accumulator columns per step, software pipelined: the TMEM loads of step i+1 are in flight while step i
             // is tested (TMEM reads are 64 B/clk/SM: 128x256 fp32 accumulators take >= 2048 clk to drain, which bounds
