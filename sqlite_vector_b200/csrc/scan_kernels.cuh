@@ -985,7 +985,7 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
     }
     // last block publishes the header and re-arms the control words for the next query.  The host only reads the
     // mapped buffers after the stream has drained, so device-scope ordering between blocks is all that is needed.
-    __shared__ int is_last, push_total;
+    __shared__ int is_last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1003,7 +1003,6 @@ __global__ void __launch_bounds__(filter_warps(FAST) * 32, 1) filter_kernel(cons
             fq.hdr[5] = fp.push.src;
             fq.hdr[6] = fp.headcap;
             fq.ctrl[0] = 0; fq.ctrl[1] = 0; fq.ctrl[2] = 0;
-            push_total = total;
         }
         is_last = last;
     }
