@@ -566,6 +566,50 @@ def main():
                                    "_result": rb}
         except Exception as ex:  # never lose the headline line
             batched_sharded = {"error": str(ex)}
+    # ---- and through REPLICAS: the column fits one GPU (n * dim bytes), so every rank holds all of it and the global batch of
+    # world x 1024 queries is split by query (shard.query_sharded_batch_topk): no exchange on the data path
+    batched_replicas = None
+    if world > 1 and not a.no_batched and n * dim <= 40e9:
+        try:
+            B = 1024
+            ixr = vs.Index(api.I8, dim, n, device=local_rank)
+            for b, a0, rows in corpus_blocks(n, 0, n):
+                x = quantize_s8(torch, gen_block_f32(torch, b, rows, dim, device), scale)
+                torch.cuda.synchronize()
+                ixr.append_device(x.data_ptr(), rows)
+                del x
+            ixr.finalize()
+            q_glob = np.concatenate([np.roll(q_host[:B], 37 * r, axis=0) for r in range(world)])      # the global batch; rank r answers [r*B, (r+1)*B)
+            shard.query_sharded_batch_topk(ixr, api.L2, q_glob, k, gather=False)                        # warm-up: row norms, tensor maps
+            barrier()
+            nb, t0b = 10, time.perf_counter()
+            for _ in range(nb):
+                (rid, rdd, rcn), (qlo, qhi) = shard.query_sharded_batch_topk(ixr, api.L2, q_glob, k, gather=False)
+            barrier()
+            dtb = (time.perf_counter() - t0b) / nb
+            t = torch.tensor([dtb], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtb = float(t.item())
+            # once more with the results all-gathered to every rank (what sharded_batch_topk / the peer exchange deliver)
+            barrier()
+            t0g = time.perf_counter()
+            for _ in range(3):
+                shard.query_sharded_batch_topk(ixr, api.L2, q_glob, k, device=device, gather=True)
+            barrier()
+            dtg = (time.perf_counter() - t0g) / 3
+            t = torch.tensor([dtg], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtg = float(t.item())
+            ixr.close()
+            batched_replicas = {"workload": f"vector_quantize_scan int8 dim={dim} n={n} k={k} L2, global batch {world} x {B} queries, column replicated on {world} GPUs",
+                                "queries_per_s": world * B / dtb, "ms_per_global_batch": dtb * 1e3, "batch_per_gpu": B, "global_batch": world * B,
+                                "queries_per_s_results_on_every_rank": world * B / dtg,
+                                "scaling": "weak in queries (each GPU answers its own 1024 of the global batch over the whole column)",
+                                "path": "shard.query_sharded_batch_topk: vsb_scan_topk (tcgen05 batch path) on this rank's query slice, host queries in, host top-k out; "
+                                        "no exchange on the data path; queries_per_s_results_on_every_rank adds one NCCL all-gather of the results",
+                                "_result": (rid, rdd, rcn, q_glob[qlo:qhi])}
+        except Exception as ex:  # never lose the headline line
+            batched_replicas = {"error": str(ex)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -645,6 +689,15 @@ def main():
                 chk.append(bool(np.array_equal(ids_ref, rb[0][b, :rb[2][b]]) and np.array_equal(d_ref, rb[1][b, :rb[2][b]])))
             batched_sharded["parity"] = {"queries_checked": [0, 511, 1023], "gpu_result_matches_reference": all(chk), "checked_against": how}
         out["batched"] = {"int8_L2_dim%d_n%d_b1024_sharded" % (dim, n): batched_sharded}
+    if batched_replicas is not None:
+        rr = batched_replicas.pop("_result", None)
+        if rr is not None and buf is not None:
+            chk = []
+            for b in (0, 511, 1023):
+                (ids_ref, d_ref), how = reference_topk_quant(buf, n, dim, k, rr[3][b])
+                chk.append(bool(np.array_equal(ids_ref, rr[0][b, :rr[2][b]]) and np.array_equal(d_ref, rr[1][b, :rr[2][b]])))
+            batched_replicas["parity"] = {"queries_checked": [0, 511, 1023], "gpu_result_matches_reference": all(chk), "checked_against": how}
+        out.setdefault("batched", {})["int8_L2_dim%d_n%d_b1024_replicas" % (dim, n)] = batched_replicas
 
     # ---- extras (N = 1): f32 single-query roofline, SQL end to end
     if world == 1 and not a.no_extras:

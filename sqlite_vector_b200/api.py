@@ -217,7 +217,9 @@ class Index:
     def finalize(self):
         self.eng.check(self.eng.lib.vsb_index_finalize(self.h))
 
-    def scan_topk(self, metric: int, queries: np.ndarray, k: int, max_index: int | None = None):
+    def scan_topk(self, metric: int, queries: np.ndarray, k: int, max_index: int | None = None, as_arrays: bool = False):
+        """top-k of one query or a batch.  Returns one (rowids, distances) pair per query, or with as_arrays the C-ABI's own
+        output (rowids[nq, k], distances[nq, k], counts[nq]) without the per-query Python objects."""
         q = np.ascontiguousarray(queries)
         q2 = q.reshape(-1, q.shape[-1]) if q.ndim > 1 else q.reshape(1, -1)
         nq = q2.shape[0]
@@ -227,6 +229,8 @@ class Index:
         mi = C.c_int(0 if max_index is None else max_index)
         self.eng.check(self.eng.lib.vsb_scan_topk(self.h, metric, _ptr(q2), nq, k, _ptr(ids), _ptr(dist), _ptr(counts),
                                                  C.byref(mi) if max_index is not None else None))
+        if as_arrays:
+            return ((ids, dist, counts), mi.value) if max_index is not None else (ids, dist, counts)
         out = [(ids[b, :counts[b]].copy(), dist[b, :counts[b]].copy()) for b in range(nq)]
         if max_index is not None:
             return out, mi.value

@@ -833,6 +833,17 @@ __global__ void merge_logs_kernel(const MergeParams mp) {
 // part of its entry-log block (header, counts, `count` entries per query) into row `src` of every target's log area and raises
 // the target's flag when all of its blocks have fenced.  grid = (targets, slices); the header travels with the shard's overflow
 // flags (stats[2]) in hdr[3], so every rank reaches the same verdict without a host round trip.
+// a few integers passed by value to device memory (headers, shard offsets): keeps pageable host copies, which can make the
+// host wait for the stream, out of the pipelined paths
+struct SmallInts { int n; long long v[16]; };
+__global__ void store_ints_kernel(long long *out64, int *out32, const SmallInts s) {
+    const int i = threadIdx.x;
+    if (i < s.n) {
+        if (out64) out64[i] = s.v[i];
+        if (out32) out32[i] = (int)s.v[i];
+    }
+}
+
 struct LogPushParams {
     const uint8_t *block;        // local entry-log block (acc_block layout)
     const unsigned *stats;       // [2] = overflow flags of this batch's levels

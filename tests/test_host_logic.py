@@ -136,6 +136,54 @@ def test_sharded_merge_gloo_world2(tmp_path):
     assert r.returncode == 0 and "SHARD_OK" in r.stdout, r.stdout + r.stderr
 
 
+QWORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sqlite_vector_b200 import shard
+from oracle import pyoracle as po
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+rng = np.random.Generator(np.random.PCG64(5))
+n, dim, k, nq = 700, 12, 7, 11                                  # 11 queries over 2 ranks: ragged slices (5 + 6)
+x = rng.integers(-3, 4, (n, dim)).astype(np.int8)
+qs = rng.integers(-3, 4, (nq, dim)).astype(np.int8)
+rowids = np.arange(n, dtype=np.int64) * 3 + 1
+orc = po.Oracle()
+class Replica:                                                   # stand-in for the full index on this rank's GPU (no device here)
+    calls = 0
+    def scan_topk(self, metric, q, kk, as_arrays=False):
+        Replica.calls += q.shape[0]
+        ids, dd, cnt = np.zeros((q.shape[0], kk), np.int64), np.zeros((q.shape[0], kk)), np.zeros(q.shape[0], np.int32)
+        for i in range(q.shape[0]):
+            ri, rd = orc.scan_dense(metric, po.I8, q[i], x, rowids, kk)
+            cnt[i] = len(ri); ids[i, :cnt[i]] = ri; dd[i, :cnt[i]] = rd
+        return ids, dd, cnt
+ids, d, cnt = shard.query_sharded_batch_topk(Replica(), po.L2, qs, k)
+b = shard.query_split(nq, world)
+assert Replica.calls == b[rank + 1] - b[rank]
+for i in range(nq):
+    wi, wd = orc.scan_dense(po.L2, po.I8, qs[i], x, rowids, k)
+    assert cnt[i] == len(wi) and np.array_equal(ids[i, :cnt[i]], wi) and np.array_equal(d[i, :cnt[i]], wd), (rank, i)
+(li, ld, lc), (lo, hi) = shard.query_sharded_batch_topk(Replica(), po.L2, qs, k, gather=False)
+assert (lo, hi) == (b[rank], b[rank + 1]) and np.array_equal(li, ids[lo:hi]) and np.array_equal(ld, d[lo:hi])
+dist.barrier()
+if rank == 0: print("QSHARD_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_query_sharded_batch_gloo_world2(tmp_path):
+    """replicas + query split: every rank answers its slice, one all-gather gives every rank all results"""
+    script = tmp_path / "qworker.py"
+    script.write_text(QWORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29614", str(script), ROOT], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "QSHARD_OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_merge_result_blocks_matches_oracle(oracle):
     """vsb_merge_result_blocks (host) over hand-built shard result blocks == the oracle's scan of the whole column"""
     import sqlite_vector_b200 as vs
