@@ -39,7 +39,6 @@ int g_opt_ring_bytes = 0;      // 0: use all shared memory left
 int g_opt_no_batch = 0;        // 1: never take the tensor-core batch path
 int g_opt_batch_debug = 0;     // 1: print per-stage timings of the batch path to stderr (serialises the stages)
 int g_opt_batch_m0 = 128;      // batch path: rows refined exhaustively before the first tensor-core level
-int g_opt_batch_ws = 2;        // process exchange, batched queries: 2 = consecutive batches use two workspaces / streams and overlap; 1 = one
 int g_opt_merge_stream = 1;    // process exchange, batched queries: wait + merge + copy back on their own stream (overlaps the next batch's levels)
 int g_opt_batch_growth = 8;    // batch path: each tensor-core level covers rows [m, growth*m) (capped by k, see batch_growth)
 int g_opt_fuse_mb = 0;         // > 0: vsb_scan_submit_group fuses a group into ONE scan launch when one query's scan reads less than this
@@ -201,7 +200,6 @@ struct vsb_index {
     long long st_queries = 0, st_survivors = 0, st_fallbacks = 0, st_last_survivors = 0;
     long long st_batches = 0, st_batch_cands = 0, st_batch_kept = 0, st_tc_us = 0, st_tc_rows = 0, st_batch_us = 0;
     void *batch = nullptr;   // BatchWs (tensor-core batch path workspace)
-    void *batch_alt = nullptr;   // second workspace with its own stream (process exchange: two batches' levels overlap)
 };
 
 namespace {
@@ -857,7 +855,6 @@ int vsb_set_option(const char *name, int value) {
     else if (!strcmp(name, "batch_m0")) p = &g_opt_batch_m0;
     else if (!strcmp(name, "batch_growth")) p = &g_opt_batch_growth;
     else if (!strcmp(name, "merge_stream")) p = &g_opt_merge_stream;
-    else if (!strcmp(name, "batch_ws")) p = &g_opt_batch_ws;
     else if (!strcmp(name, "batch_debug")) p = &g_opt_batch_debug;
     else if (!strcmp(name, "scan_streams")) p = &g_opt_scan_streams;
     else if (!strcmp(name, "xwait_ms")) p = &g_opt_xwait_ms;

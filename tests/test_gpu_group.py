@@ -252,12 +252,11 @@ for metric, kk in ((api.L2, 20), (api.COSINE, 100), (api.DOT, 7)):
     for b in range(70):
         want_ids, want_d = orc.scan_dense(metric, po.I8, qb[b], x, rowids, kk)
         assert np.array_equal(res[b][0], want_ids) and np.array_equal(res[b][1], want_d), (rank, "batch", metric, b)
-# a longer pipeline (buffers, workspaces and streams are reused), in the three stream layouts: two workspaces + merge stream
-# (default), one workspace + merge stream, everything on the engine stream
+# a longer pipeline (the buffers are reused): merge on its own stream (default) and everything on the engine stream
 qp = rng.integers(-6, 7, (7, 24, dim)).astype(np.int8)
 want_p = [[orc.scan_dense(po.L2, po.I8, qp[j, b], x, rowids, 10) for b in range(24)] for j in range(7)]
-for ws, ms in ((2, 1), (1, 1), (1, 0)):
-    eng.set_option("batch_ws", ws); eng.set_option("merge_stream", ms)
+for ms in (1, 0):
+    eng.set_option("merge_stream", ms)
     got, pend = [], None
     for j in range(7):
         t = exch.batch_submit(api.L2, qp[j], 10)
@@ -267,8 +266,8 @@ for ws, ms in ((2, 1), (1, 1), (1, 0)):
     got.append(exch.batch_finish(pend))
     for j in range(7):
         for b in range(24):
-            assert np.array_equal(got[j][b][0], want_p[j][b][0]) and np.array_equal(got[j][b][1], want_p[j][b][1]), (rank, "pipeline", ws, ms, j, b)
-eng.set_option("batch_ws", 2); eng.set_option("merge_stream", 1)
+            assert np.array_equal(got[j][b][0], want_p[j][b][0]) and np.array_equal(got[j][b][1], want_p[j][b][1]), (rank, "pipeline", ms, j, b)
+eng.set_option("merge_stream", 1)
 # a shard-local capacity overflow (descending distances: every row enters the slots) must reach EVERY rank as ERANGE
 xo = np.zeros((n, 16), dtype=np.int8)
 xo[:, 0] = np.clip((n - 1 - np.arange(n)) // 1600, 0, 124).astype(np.int8)
