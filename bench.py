@@ -870,7 +870,7 @@ def sql_e2e_leg(n=200_000, queries=30):
     out = {"n": n, "dim": 384, "k": 20, "queries": queries}
     for r in rows:
         tag = "ours" if "sqlite_vector_b200" in r.get("lib", "") else "reference_avx2"
-        out[tag] = {kk: r.get(kk) for kk in ("backend", "quantize_s", "preload_s", "quantize_scan_ms", "full_scan_ms", "quantize_scan_ids_crc", "error") if r.get(kk) is not None}
+        out[tag] = {kk: r.get(kk) for kk in ("backend", "first_use_s", "quantize_s", "preload_s", "quantize_scan_ms", "full_scan_ms", "quantize_scan_ids_crc", "error") if r.get(kk) is not None}
     if "ours" in out and "reference_avx2" in out and "quantize_scan_ms" in out["ours"] and "quantize_scan_ms" in out["reference_avx2"]:
         out["same_quantize_scan_ids"] = out["ours"].get("quantize_scan_ids_crc") == out["reference_avx2"].get("quantize_scan_ids_crc")
     return out
