@@ -244,3 +244,22 @@ def test_merge_result_groups_matches_oracle(oracle):
     for j in range(G):
         want_ids, want_d = oracle.scan_dense(po.L2, po.I8, qs[j], x, np.arange(1, n + 1, dtype=np.int64), k)
         assert np.array_equal(res[j][0], want_ids) and np.array_equal(res[j][1], want_d), j
+
+
+def test_built_kernels_use_tcgen05_and_tma_not_mma_sync():
+    """the library that travels to the GPU box: tensor-core kernels are tcgen05 (UTC*MMA + TMEM loads + TMA tensor loads), the
+    scan kernels use TMA bulk copies, nothing falls back to mma.sync (tools/sass_evidence.py over cuobjdump -sass)"""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("no cuobjdump here")
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_evidence.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ev = json.loads(r.stdout)
+    ks = ev["kernels"]
+    tc = [k for k in ks if "tc_scan_kernel" in k]
+    assert len(tc) >= 24 and all(("UTCIMMA" in ks[k] or "UTCHMMA" in ks[k]) and "UTMALDG" in ks[k] and "LDTM" in ks[k] and "UTCBAR" in ks[k] for k in tc), tc
+    staged = [k for k in ks if "scan_kernel<" in k and "tc_" not in k and k.rstrip(">").endswith("false")]
+    assert len(staged) == 20 and all("UBLKCP" in ks[k] for k in staged), staged
+    assert not ev["mma_sync_anywhere"]
+    assert all("tc_scan_kernel" not in k and "scan_kernel<" not in k for k in ev["local_memory_spills"]), ev["local_memory_spills"]
