@@ -9,7 +9,7 @@ print("roofline", {k: d["roofline"].get(k) for k in ("achieved", "peak", "frac",
 print("clocks", d.get("clocks"))
 for k, v in (d.get("batched") or {}).items():
     if isinstance(v, dict):
-        print("batched", k, {kk: v.get(kk) for kk in ("queries_per_s", "ms_per_batch", "parity")}, (v.get("roofline") or {}).get("achieved"), (v.get("roofline") or {}).get("frac"))
+        print("batched", k, {kk: v.get(kk) for kk in ("queries_per_s", "ms_per_batch", "ms_per_global_batch", "queries_per_s_results_on_every_rank", "parity", "error") if v.get(kk) is not None}, (v.get("roofline") or {}).get("achieved"), (v.get("roofline") or {}).get("frac"))
 for k in ("fp_single_query", "sql_e2e", "cpu_baseline", "parity"):
     if d.get(k) is not None:
         print(k, d[k])
