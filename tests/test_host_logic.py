@@ -168,6 +168,13 @@ for i in range(nq):
     assert cnt[i] == len(wi) and np.array_equal(ids[i, :cnt[i]], wi) and np.array_equal(d[i, :cnt[i]], wd), (rank, i)
 (li, ld, lc), (lo, hi) = shard.query_sharded_batch_topk(Replica(), po.L2, qs, k, gather=False)
 assert (lo, hi) == (b[rank], b[rank + 1]) and np.array_equal(li, ids[lo:hi]) and np.array_equal(ld, d[lo:hi])
+# fewer queries than ranks: the empty slice takes part in the gather without touching its replica
+calls0 = Replica.calls
+i1, d1, c1 = shard.query_sharded_batch_topk(Replica(), po.DOT, qs[:1], 3)
+assert i1.shape == (1, 3) and Replica.calls - calls0 == (1 if rank == world - 1 else 0)
+wi, wd = orc.scan_dense(po.DOT, po.I8, qs[0], x, rowids, 3)
+assert np.array_equal(i1[0, :c1[0]], wi) and np.array_equal(d1[0, :c1[0]], wd)
+assert shard.query_split(1, 2) == [0, 0, 1] and shard.query_split(10, 4) == [0, 2, 5, 7, 10]
 dist.barrier()
 if rank == 0: print("QSHARD_OK")
 dist.destroy_process_group()
